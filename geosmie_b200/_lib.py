@@ -1,0 +1,242 @@
+"""ctypes binding of libgeosmie_b200.so (C ABI: include/geosmie_b200.h).  No CPU fallback -- fails loudly."""
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgeosmie_b200.so")
+
+GM_NSCAL = 11
+S_W, S_X2W, S_X3W, S_X4W, S_QEXT, S_QSCA, S_QABS, S_QB, S_G, S_CSCA, S_CEXT = range(11)
+F_ELIDE_ZERO_WEIGHT = 1
+
+_lib = None
+_lock = threading.Lock()
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int32)
+c_lp = C.POINTER(C.c_int64)
+vp = C.c_void_p
+
+# every symbol include/geosmie_b200.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    "gm_version": (C.c_int, []),
+    "gm_last_error": (C.c_char_p, []),
+    "gm_init": (C.c_int, [C.c_int, C.POINTER(vp)]),
+    "gm_destroy": (C.c_int, [vp]),
+    "gm_set_stream": (C.c_int, [vp, vp]),
+    "gm_sync": (C.c_int, [vp]),
+    "gm_launch_count": (C.c_int64, [vp]),
+    "gm_mie_eval": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp]),
+    "gm_table_create": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, vp, C.POINTER(vp)]),
+    "gm_table_destroy": (C.c_int, [vp]),
+    "gm_table_nx": (C.c_int, [vp]),
+    "gm_table_nang": (C.c_int, [vp]),
+    "gm_table_set_bessel": (C.c_int, [vp, vp, vp, vp]),
+    "gm_table_run": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int, vp, vp]),
+    "gm_table_run_dev": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int, vp, vp]),
+    "gm_table_particles": (C.c_int, [vp, C.c_int, vp, vp, vp, vp]),
+    "gm_table_last_stats": (C.c_int, [vp, vp]),
+    "gm_table_set_timing": (C.c_int, [vp, C.c_int]),
+    "gm_table_last_kernel_ms": (C.c_int, [vp, c_dp, c_dp, c_dp]),
+    "gm_gsf_expand": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int]),
+    "gm_gsf_expand_dev": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int]),
+    "gm_band_average": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int, vp]),
+}
+
+
+class GeosmieError(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen the library and bind every symbol of the header.  Works without a GPU (no compute is run)."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise GeosmieError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` or "
+                               "`make -C geosmie_b200/csrc` -- there is no CPU fallback" % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise GeosmieError("libgeosmie_b200 error %d: %s" % (rc, load().gm_last_error().decode()))
+
+
+def f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def ptr(a):
+    return None if a is None else a.ctypes.data_as(vp)
+
+
+class Handle:
+    """One per GPU.  `Handle.get(device)` returns a cached instance."""
+    _cache = {}
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = vp()
+        check(self.lib.gm_init(int(device), C.byref(h)))
+        self.h = h
+        self.device = device
+
+    @classmethod
+    def get(cls, device=None):
+        if device is None:
+            device = int(os.environ.get("GEOSMIE_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        if device not in cls._cache:
+            cls._cache[device] = cls(device)
+        return cls._cache[device]
+
+    def set_stream(self, stream_ptr):
+        check(self.lib.gm_set_stream(self.h, vp(stream_ptr)))
+
+    def sync(self):
+        check(self.lib.gm_sync(self.h))
+
+    def launch_count(self):
+        return int(self.lib.gm_launch_count(self.h))
+
+    # ---- per-particle Mie ------------------------------------------------------------------------------------------
+    def mie_eval(self, x, mz, mrel, nmax, u=None, xcore=None, ajv=None, ayv=None, want_s12=True, want_ab=False):
+        x = f64(np.atleast_1d(x))
+        n = x.size
+        nmax = i32(np.atleast_1d(nmax))
+        mz = np.ascontiguousarray(np.atleast_1d(mz), dtype=np.complex128)
+        mrel = np.ascontiguousarray(np.atleast_1d(mrel), dtype=np.complex128)
+        stride = 1 if mz.size > 1 else 0
+        if stride and (mz.size != n or mrel.size != n):
+            raise ValueError("per-particle materials must have one entry per particle")
+        q = np.empty((n, 6))
+        nang = 0
+        uu = None
+        s12 = None
+        if u is not None and want_s12:
+            uu = f64(np.atleast_1d(u))
+            nang = uu.size
+            s12 = np.empty((n, nang, 4))
+        ab = np.empty((int(nmax.sum()), 4)) if want_ab else None
+        xc = f64(np.atleast_1d(xcore)) if xcore is not None else None
+        off = jv = yv = None
+        if ajv is not None and ayv is not None:
+            jv, yv = f64(ajv), f64(ayv)
+            off = i64(np.concatenate([[0], np.cumsum(nmax)[:-1]]))
+        check(self.lib.gm_mie_eval(self.h, n, ptr(x), ptr(xc), ptr(mz), ptr(mrel), stride, ptr(nmax), ptr(off), ptr(jv), ptr(yv),
+                                   nang, ptr(uu), ptr(q), ptr(s12), ptr(ab)))
+        return q, s12, ab
+
+    # ---- GSF / bands -----------------------------------------------------------------------------------------------
+    def gsf_expand(self, ang_deg, F, ng=129, quantize10=False):
+        ang = f64(ang_deg)
+        F = f64(F)
+        ncell = F.shape[0]
+        assert F.shape[1:] == (6, ang.size)
+        coef = np.empty((ncell, 6, ng))
+        cnorm = np.empty(ncell)
+        check(self.lib.gm_gsf_expand(self.h, ncell, ang.size, ptr(ang), ptr(F), ng, ptr(coef), ptr(cnorm), int(bool(quantize10))))
+        return coef, cnorm
+
+    def band_average(self, lam, v, lo, hi, use_wavenum):
+        lam, v, lo, hi = f64(lam), f64(v), f64(lo), f64(hi)
+        ncol = v.shape[0]
+        out = np.empty((ncol, lo.size))
+        check(self.lib.gm_band_average(self.h, ncol, lam.size, ptr(lam), ptr(v), lo.size, ptr(lo), ptr(hi), int(bool(use_wavenum)), ptr(out)))
+        return out
+
+
+class Table:
+    """Per-bin device object (x grid, nmax, Riccati-Bessel and pi/tau tables); wraps gm_table_*."""
+
+    def __init__(self, x, nmax, cos_theta, handle=None):
+        self.handle = handle or Handle.get()
+        self.lib = self.handle.lib
+        self.x = f64(x)
+        self.nmax = i32(nmax)
+        self.cost = f64(cos_theta)
+        t = vp()
+        check(self.lib.gm_table_create(self.handle.h, self.x.size, ptr(self.x), ptr(self.nmax), self.cost.size, ptr(self.cost), C.byref(t)))
+        self.t = t
+        self.nx = self.x.size
+        self.nang = self.cost.size
+
+    def close(self):
+        if getattr(self, "t", None):
+            self.lib.gm_table_destroy(self.t)
+            self.t = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_bessel(self, jv_half, yv_half):
+        off = i64(np.concatenate([[0], np.cumsum(self.nmax + 1)[:-1]]))
+        check(self.lib.gm_table_set_bessel(self.t, ptr(off), ptr(f64(jv_half)), ptr(f64(yv_half))))
+
+    def run(self, mz, mrel, w_phase, w_scal=None, elide=False):
+        """Host-buffer call.  Returns (scal [ntask][nmode][11], phase [ntask][4][nang])."""
+        mz = np.ascontiguousarray(np.atleast_1d(mz), dtype=np.complex128)
+        mrel = np.ascontiguousarray(np.atleast_1d(mrel), dtype=np.complex128)
+        ntask = mz.size
+        wp = f64(w_phase).reshape(ntask, self.nx)
+        nmode = 1
+        ws = None
+        if w_scal is not None:
+            ws = f64(w_scal)
+            nmode = ws.shape[1]
+            assert ws.shape == (ntask, nmode, self.nx)
+        scal = np.empty((ntask, nmode, GM_NSCAL))
+        phase = np.empty((ntask, 4, self.nang))
+        check(self.lib.gm_table_run(self.t, ntask, ptr(mz), ptr(mrel), nmode, ptr(wp), ptr(ws), F_ELIDE_ZERO_WEIGHT if elide else 0,
+                                    ptr(scal), ptr(phase)))
+        return scal, phase
+
+    def run_dev(self, ntask, mz_ptr, mrel_ptr, nmode, wphase_ptr, wscal_ptr, out_scal_ptr, out_phase_ptr, elide=False):
+        """Device-pointer call (asynchronous on the handle's stream); pointers are integers (tensor.data_ptr())."""
+        check(self.lib.gm_table_run_dev(self.t, ntask, vp(mz_ptr), vp(mrel_ptr), nmode, vp(wphase_ptr),
+                                        vp(wscal_ptr) if wscal_ptr else None, F_ELIDE_ZERO_WEIGHT if elide else 0,
+                                        vp(out_scal_ptr), vp(out_phase_ptr)))
+
+    def particles(self, mz, mrel, want_s12=True):
+        mz = np.ascontiguousarray(np.atleast_1d(mz), dtype=np.complex128)
+        mrel = np.ascontiguousarray(np.atleast_1d(mrel), dtype=np.complex128)
+        ntask = mz.size
+        q = np.empty((ntask, self.nx, 6))
+        s12 = np.empty((ntask, self.nx, self.nang, 4)) if want_s12 else None
+        check(self.lib.gm_table_particles(self.t, ntask, ptr(mz), ptr(mrel), ptr(q), ptr(s12)))
+        return q, s12
+
+    def last_stats(self):
+        s = np.zeros(8)
+        check(self.lib.gm_table_last_stats(self.t, ptr(s)))
+        return {"evals": s[0], "sum_nmax": s[1], "sum_nmx": s[2], "k4_groups": s[3], "launches": s[4]}
+
+    def set_timing(self, on=True):
+        check(self.lib.gm_table_set_timing(self.t, int(on)))
+
+    def last_kernel_ms(self):
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        check(self.lib.gm_table_last_kernel_ms(self.t, C.byref(a), C.byref(b), C.byref(c)))
+        return {"coeff": a.value, "contract": b.value, "finalize": c.value}

@@ -1,0 +1,579 @@
+// gm_api.cu -- host side of the C ABI declared in include/geosmie_b200.h (lifetime, per-particle Mie, table cells).
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+
+#include "gm_mie_kernels.cuh"
+#include "gm_coated.cuh"
+
+// ------------------------------------------------------------------------------------------------ errors / lifetime
+static thread_local char g_err[512] = "";
+
+void gm_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* gm_last_error(void) { return g_err; }
+extern "C" int gm_version(void) { return 100; }
+
+extern "C" int gm_init(int device, gm_handle_t* out) {
+  GM_REQUIRE(out != nullptr, "out handle pointer is NULL");
+  int ndev = 0;
+  GM_CUDA_TRY(cudaGetDeviceCount(&ndev));
+  GM_REQUIRE(device >= 0 && device < ndev, "device index out of range");
+  GM_CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  GM_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    gm_set_error("libgeosmie_b200 is built for sm_100a only; device %d is sm_%d%d (%s)", device, prop.major, prop.minor, prop.name);
+    return GM_ECUDA;
+  }
+  gm_handle_s* h = new gm_handle_s();
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  // opt in to the large dynamic shared memory of the contraction kernels once
+  const int smem = GM_STAGES * GM_STAGE_DBL * 8 + 2 * GM_STAGES * 8;
+  GM_CUDA_TRY(cudaFuncSetAttribute(k_contract<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  GM_CUDA_TRY(cudaFuncSetAttribute(k_contract<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  *out = h;
+  return GM_OK;
+}
+
+extern "C" int gm_destroy(gm_handle_t h) {
+  if (!h) return GM_OK;
+  cudaSetDevice(h->device);
+  for (auto& b : h->ws) b.release();
+  delete h;
+  return GM_OK;
+}
+
+extern "C" int gm_set_stream(gm_handle_t h, void* s) {
+  GM_REQUIRE(h != nullptr, "handle is NULL");
+  h->stream = reinterpret_cast<cudaStream_t>(s);
+  return GM_OK;
+}
+
+extern "C" int gm_sync(gm_handle_t h) {
+  GM_REQUIRE(h != nullptr, "handle is NULL");
+  GM_CUDA_TRY(cudaSetDevice(h->device));
+  GM_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return GM_OK;
+}
+
+extern "C" int64_t gm_launch_count(gm_handle_t h) { return h ? h->launches : 0; }
+
+#define GM_LAUNCH_CHECK(h)               \
+  do {                                   \
+    (h)->launches++;                     \
+    GM_CUDA_TRY(cudaGetLastError());     \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------ grouping
+// Host description of how a particle list is cut into groups of 32 (one warp of k_coeff, one N-extent of k_contract).
+struct Groups {
+  int nx = 0, ngroup = 0, nmaxmax = 0;
+  std::vector<long long> gboff;  // Bessel-table offset (doubles) of group g
+  std::vector<int> gk4, grow;    // DMMA k4 steps and first coefficient row of group g
+  long long bessel_len = 0;      // doubles per Bessel table
+  long long task_rows = 0;       // coefficient rows per task
+  void build(int n, const int32_t* nmax) {
+    nx = n;
+    ngroup = (n + GM_GROUP - 1) / GM_GROUP;
+    gboff.resize(ngroup);
+    gk4.resize(ngroup);
+    grow.resize(ngroup);
+    bessel_len = 0;
+    task_rows = 0;
+    nmaxmax = 0;
+    for (int g = 0; g < ngroup; ++g) {
+      int gm = 0;
+      for (int i = g * GM_GROUP; i < std::min(n, (g + 1) * GM_GROUP); ++i) gm = std::max(gm, (int)nmax[i]);
+      nmaxmax = std::max(nmaxmax, gm);
+      gboff[g] = bessel_len;
+      bessel_len += (long long)(gm + 1) * GM_GROUP;
+      gk4[g] = (gm + GM_KSTEP - 1) / GM_KSTEP;
+      grow[g] = (int)task_rows;
+      task_rows += (long long)gk4[g] * GM_KSTEP;
+    }
+  }
+};
+
+struct DevGroups {
+  DevBuf x, nmax, gboff, gk4, grow, psi, chi;
+  int upload(const Groups& G, const double* hx, const int32_t* hnmax, cudaStream_t st) {
+    int rc;
+    if ((rc = x.ensure(sizeof(double) * G.nx))) return rc;
+    if ((rc = nmax.ensure(sizeof(int) * G.nx))) return rc;
+    if ((rc = gboff.ensure(sizeof(long long) * G.ngroup))) return rc;
+    if ((rc = gk4.ensure(sizeof(int) * G.ngroup))) return rc;
+    if ((rc = grow.ensure(sizeof(int) * G.ngroup))) return rc;
+    if ((rc = psi.ensure(sizeof(double) * G.bessel_len))) return rc;
+    if ((rc = chi.ensure(sizeof(double) * G.bessel_len))) return rc;
+    GM_CUDA_TRY(cudaMemcpyAsync(x.p, hx, sizeof(double) * G.nx, cudaMemcpyHostToDevice, st));
+    GM_CUDA_TRY(cudaMemcpyAsync(nmax.p, hnmax, sizeof(int) * G.nx, cudaMemcpyHostToDevice, st));
+    GM_CUDA_TRY(cudaMemcpyAsync(gboff.p, G.gboff.data(), sizeof(long long) * G.ngroup, cudaMemcpyHostToDevice, st));
+    GM_CUDA_TRY(cudaMemcpyAsync(gk4.p, G.gk4.data(), sizeof(int) * G.ngroup, cudaMemcpyHostToDevice, st));
+    GM_CUDA_TRY(cudaMemcpyAsync(grow.p, G.grow.data(), sizeof(int) * G.ngroup, cudaMemcpyHostToDevice, st));
+    GM_CUDA_TRY(cudaMemsetAsync(psi.p, 0, sizeof(double) * G.bessel_len, st));
+    GM_CUDA_TRY(cudaMemsetAsync(chi.p, 0, sizeof(double) * G.bessel_len, st));
+    return GM_OK;
+  }
+  void release() {
+    x.release(); nmax.release(); gboff.release(); gk4.release(); grow.release(); psi.release(); chi.release();
+  }
+};
+
+static int check_particles(int n, const double* x, const int32_t* nmax) {
+  GM_REQUIRE(n > 0, "need at least one particle");
+  GM_REQUIRE(x && nmax, "x / nmax is NULL");
+  for (int i = 0; i < n; ++i) {
+    GM_REQUIRE(x[i] > 0.0 && std::isfinite(x[i]), "size parameters must be finite and > 0");
+    GM_REQUIRE(nmax[i] >= 1 && nmax[i] < (1 << 20), "nmax out of range");
+  }
+  return GM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ gm_mie_eval
+extern "C" int gm_mie_eval(gm_handle_t h, int n, const double* x, const double* xcore, const double* mz, const double* mrel,
+                           int mat_stride, const int32_t* nmax, const int64_t* bes_off, const double* ajv, const double* ayv,
+                           int nang, const double* u, double* q, double* s12, double* ab) {
+  GM_REQUIRE(h != nullptr, "handle is NULL");
+  GM_REQUIRE(mz && mrel, "material arrays are NULL");
+  GM_REQUIRE(mat_stride == 0 || mat_stride == 1, "mat_stride must be 0 or 1");
+  GM_REQUIRE(nang >= 0 && (nang == 0 || u), "u is NULL");
+  GM_REQUIRE(!s12 || nang > 0, "s12 requested without angles");
+  int rc = check_particles(n, x, nmax);
+  if (rc) return rc;
+  GM_CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+
+  Groups G;
+  G.build(n, nmax);
+  std::vector<long long> aboff(n + 1, 0);
+  for (int i = 0; i < n; ++i) aboff[i + 1] = aboff[i] + nmax[i];
+  const long long nab = aboff[n];
+
+  // workspace slots: 0 x,1 nmax,2 gboff,3 psi,4 chi,5 mz,6 mrel,7 aboff,8 ab,9 q,10 u,11 s12,12 jv,13 yv,14 besoff,15 xcore
+  DevBuf* W = h->ws;
+  const int nmat = mat_stride ? n : 1;
+  if ((rc = W[0].ensure(sizeof(double) * n)) || (rc = W[1].ensure(sizeof(int) * n)) ||
+      (rc = W[2].ensure(sizeof(long long) * G.ngroup)) || (rc = W[3].ensure(sizeof(double) * G.bessel_len)) ||
+      (rc = W[4].ensure(sizeof(double) * G.bessel_len)) || (rc = W[5].ensure(sizeof(double2) * nmat)) ||
+      (rc = W[6].ensure(sizeof(double2) * nmat)) || (rc = W[7].ensure(sizeof(long long) * (n + 1))) ||
+      (rc = W[8].ensure(sizeof(double4) * nab)) || (rc = W[9].ensure(sizeof(double) * 6 * n)))
+    return rc;
+  GM_CUDA_TRY(cudaMemcpyAsync(W[0].p, x, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  GM_CUDA_TRY(cudaMemcpyAsync(W[1].p, nmax, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+  GM_CUDA_TRY(cudaMemcpyAsync(W[2].p, G.gboff.data(), sizeof(long long) * G.ngroup, cudaMemcpyHostToDevice, st));
+  GM_CUDA_TRY(cudaMemcpyAsync(W[5].p, mz, sizeof(double2) * nmat, cudaMemcpyHostToDevice, st));
+  GM_CUDA_TRY(cudaMemcpyAsync(W[6].p, mrel, sizeof(double2) * nmat, cudaMemcpyHostToDevice, st));
+  GM_CUDA_TRY(cudaMemcpyAsync(W[7].p, aboff.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, st));
+
+  if (xcore) {
+    // coated spheres: coated_mie_coeff, mie_coeffs.py:183-251
+    if ((rc = W[15].ensure(sizeof(double) * n))) return rc;
+    GM_CUDA_TRY(cudaMemcpyAsync(W[15].p, xcore, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    // per-particle scratch: 3 D arrays + psi/chi at v, w (complex) and y (real)
+    std::vector<long long> soff(n + 1, 0);
+    for (int i = 0; i < n; ++i) soff[i + 1] = soff[i] + (long long)(nmax[i] + 1);
+    if ((rc = W[3].ensure(sizeof(double) * 16 * soff[n]))) return rc;
+    if ((rc = W[2].ensure(sizeof(long long) * (n + 1)))) return rc;
+    GM_CUDA_TRY(cudaMemcpyAsync(W[2].p, soff.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, st));
+    k_coated_coeff<<<(n + 63) / 64, 64, 0, st>>>(n, W[15].as<double>(), W[0].as<double>(), W[5].as<double2>(), W[6].as<double2>(),
+                                                  mat_stride, W[1].as<int>(), W[2].as<long long>(), W[3].as<double>(),
+                                                  W[7].as<long long>(), W[8].as<double4>());
+    GM_LAUNCH_CHECK(h);
+    k_props_nat<<<(n + 127) / 128, 128, 0, st>>>(n, W[0].as<double>(), W[1].as<int>(), W[7].as<long long>(), W[8].as<double4>(),
+                                                 W[9].as<double>());
+    GM_LAUNCH_CHECK(h);
+  } else {
+    GM_CUDA_TRY(cudaMemsetAsync(W[3].p, 0, sizeof(double) * G.bessel_len, st));
+    GM_CUDA_TRY(cudaMemsetAsync(W[4].p, 0, sizeof(double) * G.bessel_len, st));
+    if (ajv && ayv) {
+      // the reference's ajv/ayv hold orders k+1.5 (k = 0..nmax-1); psi_0, chi_0 come from sin/cos (mie_coeffs.py:108,112)
+      GM_REQUIRE(bes_off != nullptr, "bes_off is NULL");
+      std::vector<long long> off(n);
+      std::vector<double> jh((size_t)nab + n), yh((size_t)nab + n);
+      long long o = 0;
+      for (int i = 0; i < n; ++i) {
+        off[i] = o;
+        jh[o] = 0.0;
+        yh[o] = 0.0;
+        for (int k = 0; k < nmax[i]; ++k) {
+          jh[o + 1 + k] = ajv[bes_off[i] + k];
+          yh[o + 1 + k] = ayv[bes_off[i] + k];
+        }
+        o += nmax[i] + 1;
+      }
+      if ((rc = W[12].ensure(sizeof(double) * jh.size())) || (rc = W[13].ensure(sizeof(double) * yh.size())) ||
+          (rc = W[14].ensure(sizeof(long long) * n)))
+        return rc;
+      GM_CUDA_TRY(cudaMemcpyAsync(W[12].p, jh.data(), sizeof(double) * jh.size(), cudaMemcpyHostToDevice, st));
+      GM_CUDA_TRY(cudaMemcpyAsync(W[13].p, yh.data(), sizeof(double) * yh.size(), cudaMemcpyHostToDevice, st));
+      GM_CUDA_TRY(cudaMemcpyAsync(W[14].p, off.data(), sizeof(long long) * n, cudaMemcpyHostToDevice, st));
+      k_bessel_from_jy<<<(n + 127) / 128, 128, 0, st>>>(n, W[0].as<double>(), W[1].as<int>(), W[2].as<long long>(),
+                                                        W[14].as<long long>(), W[12].as<double>(), W[13].as<double>(),
+                                                        W[3].as<double>(), W[4].as<double>());
+      GM_LAUNCH_CHECK(h);
+      GM_CUDA_TRY(cudaStreamSynchronize(st));  // jh/yh/off are stack-owned
+    } else {
+      k_bessel<<<(n + 127) / 128, 128, 0, st>>>(n, W[0].as<double>(), W[1].as<int>(), W[2].as<long long>(), W[3].as<double>(),
+                                                W[4].as<double>());
+      GM_LAUNCH_CHECK(h);
+    }
+    CoeffArgs A;
+    memset(&A, 0, sizeof(A));
+    A.nx = n;
+    A.ngroup = G.ngroup;
+    A.x = W[0].as<double>();
+    A.nmax = W[1].as<int>();
+    A.psi = W[3].as<double>();
+    A.chi = W[4].as<double>();
+    A.gboff = W[2].as<long long>();
+    A.mz = W[5].as<double2>();
+    A.mrel = W[6].as<double2>();
+    A.mat_per_particle = mat_stride;
+    A.aboff = W[7].as<long long>();
+    A.ab = W[8].as<double4>();
+    A.q = W[9].as<double>();
+    dim3 grid((G.ngroup + 3) / 4, 1);
+    k_coeff<1><<<grid, 128, 0, st>>>(A);
+    GM_LAUNCH_CHECK(h);
+  }
+  if (s12) {
+    if ((rc = W[10].ensure(sizeof(double) * nang)) || (rc = W[11].ensure(sizeof(double) * 4 * (size_t)n * nang))) return rc;
+    GM_CUDA_TRY(cudaMemcpyAsync(W[10].p, u, sizeof(double) * nang, cudaMemcpyHostToDevice, st));
+    k_s12_direct<<<(n + 3) / 4, 128, 0, st>>>(n, W[1].as<int>(), W[7].as<long long>(), W[8].as<double4>(), nang, W[10].as<double>(),
+                                              W[11].as<double>());
+    GM_LAUNCH_CHECK(h);
+    GM_CUDA_TRY(cudaMemcpyAsync(s12, W[11].p, sizeof(double) * 4 * (size_t)n * nang, cudaMemcpyDeviceToHost, st));
+  }
+  if (q) GM_CUDA_TRY(cudaMemcpyAsync(q, W[9].p, sizeof(double) * 6 * n, cudaMemcpyDeviceToHost, st));
+  if (ab) GM_CUDA_TRY(cudaMemcpyAsync(ab, W[8].p, sizeof(double4) * nab, cudaMemcpyDeviceToHost, st));
+  GM_CUDA_TRY(cudaStreamSynchronize(st));
+  return GM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ tables
+struct gm_table_s {
+  gm_handle_t h = nullptr;
+  int nx = 0, nang = 0, nrows = 0;
+  Groups G;
+  DevGroups D;
+  std::vector<double> hx;
+  std::vector<int32_t> hnmax;
+  DevBuf T, cost;
+  // per-run buffers
+  DevBuf coef, gact, scal_part, part, chunk_start, mz, mrel, wphase, wscal, out_scal, out_phase, stats, q, s12;
+  double last_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int timing = 0;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  double ms_coeff = 0, ms_contract = 0, ms_finalize = 0;
+};
+
+extern "C" int gm_table_create(gm_handle_t h, int nx, const double* x, const int32_t* nmax, int nang, const double* cos_theta,
+                               gm_table_t* out) {
+  GM_REQUIRE(h != nullptr && out != nullptr, "handle / out is NULL");
+  GM_REQUIRE(nang > 0 && nang <= GM_NANG_PAD, "nang must be in [1, 384]");
+  GM_REQUIRE(cos_theta != nullptr, "cos_theta is NULL");
+  int rc = check_particles(nx, x, nmax);
+  if (rc) return rc;
+  GM_CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  gm_table_s* t = new gm_table_s();
+  t->h = h;
+  t->nx = nx;
+  t->nang = nang;
+  t->hx.assign(x, x + nx);
+  t->hnmax.assign(nmax, nmax + nx);
+  t->G.build(nx, nmax);
+  t->nrows = ((t->G.nmaxmax + GM_KSTEP - 1) / GM_KSTEP) * GM_KSTEP;
+  if ((rc = t->D.upload(t->G, x, nmax, st)) || (rc = t->cost.ensure(sizeof(double) * nang)) ||
+      (rc = t->T.ensure(sizeof(double) * GM_NHALF * (size_t)t->nrows * GM_TROW))) {
+    delete t;
+    return rc;
+  }
+  GM_CUDA_TRY(cudaMemcpyAsync(t->cost.p, cos_theta, sizeof(double) * nang, cudaMemcpyHostToDevice, st));
+  GM_CUDA_TRY(cudaMemsetAsync(t->T.p, 0, sizeof(double) * GM_NHALF * (size_t)t->nrows * GM_TROW, st));
+  k_bessel<<<(nx + 127) / 128, 128, 0, st>>>(nx, t->D.x.as<double>(), t->D.nmax.as<int>(), t->D.gboff.as<long long>(),
+                                             t->D.psi.as<double>(), t->D.chi.as<double>());
+  GM_LAUNCH_CHECK(h);
+  k_pt_table<<<(GM_NANG_PAD + 127) / 128, 128, 0, st>>>(nang, t->cost.as<double>(), t->nrows, t->T.as<double>());
+  GM_LAUNCH_CHECK(h);
+  GM_CUDA_TRY(cudaStreamSynchronize(st));
+  *out = t;
+  return GM_OK;
+}
+
+extern "C" int gm_table_destroy(gm_table_t t) {
+  if (!t) return GM_OK;
+  cudaSetDevice(t->h->device);
+  t->D.release();
+  for (DevBuf* b : {&t->T, &t->cost, &t->coef, &t->gact, &t->scal_part, &t->part, &t->chunk_start, &t->mz, &t->mrel, &t->wphase,
+                    &t->wscal, &t->out_scal, &t->out_phase, &t->stats, &t->q, &t->s12})
+    b->release();
+  for (auto& e : t->ev)
+    if (e) cudaEventDestroy(e);
+  delete t;
+  return GM_OK;
+}
+
+extern "C" int gm_table_nx(gm_table_t t) { return t ? t->nx : 0; }
+extern "C" int gm_table_nang(gm_table_t t) { return t ? t->nang : 0; }
+
+extern "C" int gm_table_set_bessel(gm_table_t t, const int64_t* off, const double* jv_half, const double* yv_half) {
+  GM_REQUIRE(t && off && jv_half && yv_half, "NULL argument");
+  gm_handle_t h = t->h;
+  GM_CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  size_t tot = 0;
+  for (int i = 0; i < t->nx; ++i) tot = std::max(tot, (size_t)off[i] + t->hnmax[i] + 1);
+  DevBuf dj, dy, doff;
+  int rc;
+  if ((rc = dj.ensure(sizeof(double) * tot)) || (rc = dy.ensure(sizeof(double) * tot)) || (rc = doff.ensure(sizeof(long long) * t->nx)))
+    return rc;
+  GM_CUDA_TRY(cudaMemcpyAsync(dj.p, jv_half, sizeof(double) * tot, cudaMemcpyHostToDevice, st));
+  GM_CUDA_TRY(cudaMemcpyAsync(dy.p, yv_half, sizeof(double) * tot, cudaMemcpyHostToDevice, st));
+  GM_CUDA_TRY(cudaMemcpyAsync(doff.p, off, sizeof(long long) * t->nx, cudaMemcpyHostToDevice, st));
+  k_bessel_from_jy<<<(t->nx + 127) / 128, 128, 0, st>>>(t->nx, t->D.x.as<double>(), t->D.nmax.as<int>(), t->D.gboff.as<long long>(),
+                                                        doff.as<long long>(), dj.as<double>(), dy.as<double>(), t->D.psi.as<double>(),
+                                                        t->D.chi.as<double>());
+  GM_LAUNCH_CHECK(h);
+  GM_CUDA_TRY(cudaStreamSynchronize(st));
+  dj.release(); dy.release(); doff.release();
+  return GM_OK;
+}
+
+extern "C" int gm_table_set_timing(gm_table_t t, int enable) {
+  GM_REQUIRE(t != nullptr, "table is NULL");
+  t->timing = enable;
+  if (enable && !t->ev[0]) {
+    GM_CUDA_TRY(cudaEventCreate(&t->ev[0]));
+    GM_CUDA_TRY(cudaEventCreate(&t->ev[1]));
+  }
+  return GM_OK;
+}
+
+extern "C" int gm_table_last_kernel_ms(gm_table_t t, double* a, double* b, double* c) {
+  GM_REQUIRE(t != nullptr, "table is NULL");
+  if (a) *a = t->ms_coeff;
+  if (b) *b = t->ms_contract;
+  if (c) *c = t->ms_finalize;
+  return GM_OK;
+}
+
+static int fetch_stats(gm_table_t t);
+
+extern "C" int gm_table_last_stats(gm_table_t t, double stats[8]) {
+  GM_REQUIRE(t && stats, "NULL argument");
+  if (t->stats.p) {
+    GM_CUDA_TRY(cudaSetDevice(t->h->device));
+    int rc = fetch_stats(t);
+    if (rc) return rc;
+  }
+  for (int i = 0; i < 8; ++i) stats[i] = t->last_stats[i];
+  return GM_OK;
+}
+
+// Core of gm_table_run: all pointers are DEVICE pointers.  per_particle != 0 selects the S1/S2-per-particle epilogue.
+static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const double* d_mrel, int nmode, const double* d_wphase,
+                          const double* d_wscal, int flags, double* d_out_scal, double* d_out_phase, double* d_q, double* d_s12,
+                          bool per_particle) {
+  gm_handle_t h = t->h;
+  cudaStream_t st = h->stream;
+  const Groups& G = t->G;
+  int rc;
+  const long long task_stride = G.task_rows * GM_SB;  // doubles
+  const size_t per_task_bytes = (size_t)task_stride * 8;
+  int tb = (int)std::max<size_t>(1, h->coef_budget_bytes / std::max<size_t>(per_task_bytes, 1));
+  tb = std::min(tb, ntask);
+  tb = std::min(tb, 32768);  // grid.y limit of k_coeff
+  // chunks: enough CTAs to fill the machine ~8x over, cost-balanced by k4 steps
+  const int want_items = 8 * h->sm_count;
+  int nchunk = (want_items + 2 * tb - 1) / (2 * tb);
+  nchunk = std::max(1, std::min(nchunk, G.ngroup));
+  std::vector<int> cstart(nchunk + 1, 0);
+  {
+    long long tot = 0;
+    for (int g = 0; g < G.ngroup; ++g) tot += G.gk4[g];
+    long long acc = 0;
+    int c = 1;
+    for (int g = 0; g < G.ngroup && c < nchunk; ++g) {
+      acc += G.gk4[g];
+      if (acc * nchunk >= tot * c) cstart[c++] = g + 1;
+    }
+    for (; c < nchunk; ++c) cstart[c] = G.ngroup;
+    cstart[nchunk] = G.ngroup;
+  }
+  if ((rc = t->coef.ensure(per_task_bytes * tb)) || (rc = t->gact.ensure((size_t)tb * G.ngroup)) ||
+      (rc = t->scal_part.ensure(sizeof(double) * (size_t)tb * nmode * G.ngroup * GM_NSCAL)) ||
+      (rc = t->part.ensure(sizeof(double) * (size_t)tb * nchunk * 4 * GM_NANG_PAD)) ||
+      (rc = t->chunk_start.ensure(sizeof(int) * (nchunk + 1))) || (rc = t->stats.ensure(sizeof(unsigned long long) * 8)))
+    return rc;
+  GM_CUDA_TRY(cudaMemcpyAsync(t->chunk_start.p, cstart.data(), sizeof(int) * (nchunk + 1), cudaMemcpyHostToDevice, st));
+  GM_CUDA_TRY(cudaMemsetAsync(t->stats.p, 0, sizeof(unsigned long long) * 8, st));
+  const int smem = GM_STAGES * GM_STAGE_DBL * 8 + 2 * GM_STAGES * 8;
+  const int64_t launches0 = h->launches;
+  t->ms_coeff = t->ms_contract = t->ms_finalize = 0;
+  float ms;
+
+  for (int t0 = 0; t0 < ntask; t0 += tb) {
+    const int nt = std::min(tb, ntask - t0);
+    CoeffArgs A;
+    memset(&A, 0, sizeof(A));
+    A.nx = G.nx;
+    A.ngroup = G.ngroup;
+    A.x = t->D.x.as<double>();
+    A.nmax = t->D.nmax.as<int>();
+    A.psi = t->D.psi.as<double>();
+    A.chi = t->D.chi.as<double>();
+    A.gboff = t->D.gboff.as<long long>();
+    A.mz = reinterpret_cast<const double2*>(d_mz) + t0;
+    A.mrel = reinterpret_cast<const double2*>(d_mrel) + t0;
+    A.mat_per_particle = 0;
+    A.wphase = d_wphase ? d_wphase + (size_t)t0 * G.nx : nullptr;
+    A.wscal = d_wscal ? d_wscal + (size_t)t0 * nmode * G.nx : nullptr;
+    A.nmode = nmode;
+    A.dense = (flags & GM_F_ELIDE_ZERO_WEIGHT) ? 0 : 1;
+    A.scale_sqrtw = per_particle ? 0 : 1;
+    A.grow = t->D.grow.as<int>();
+    A.gk4 = t->D.gk4.as<int>();
+    A.coef = t->coef.as<double>();
+    A.task_stride = task_stride;
+    A.gact = t->gact.as<unsigned char>();
+    A.scal_part = t->scal_part.as<double>();
+    A.q = d_q ? d_q + (size_t)t0 * G.nx * 6 : nullptr;
+    A.stats = t->stats.as<unsigned long long>();
+    if (t->timing) GM_CUDA_TRY(cudaEventRecord(t->ev[0], st));
+    k_coeff<0><<<dim3((G.ngroup + 3) / 4, nt), 128, 0, st>>>(A);
+    GM_LAUNCH_CHECK(h);
+    if (t->timing) {
+      GM_CUDA_TRY(cudaEventRecord(t->ev[1], st));
+      GM_CUDA_TRY(cudaEventSynchronize(t->ev[1]));
+      GM_CUDA_TRY(cudaEventElapsedTime(&ms, t->ev[0], t->ev[1]));
+      t->ms_coeff += ms;
+    }
+
+    ContractArgs C;
+    memset(&C, 0, sizeof(C));
+    C.ntask = nt;
+    C.ngroup = G.ngroup;
+    C.nchunk = nchunk;
+    C.nrows = t->nrows;
+    C.T = t->T.as<double>();
+    C.coef = t->coef.as<double>();
+    C.task_stride = task_stride;
+    C.grow = t->D.grow.as<int>();
+    C.gk4 = t->D.gk4.as<int>();
+    C.gact = t->gact.as<unsigned char>();
+    C.chunk_start = t->chunk_start.as<int>();
+    C.part = t->part.as<double>();
+    C.nx = G.nx;
+    C.nang = t->nang;
+    C.s12 = d_s12 ? d_s12 + (size_t)t0 * G.nx * t->nang * 4 : nullptr;
+    if (t->timing) GM_CUDA_TRY(cudaEventRecord(t->ev[0], st));
+    if (per_particle)
+      k_contract<true><<<nt * 2 * nchunk, GM_CONTRACT_WARPS * 32, smem, st>>>(C);
+    else
+      k_contract<false><<<nt * 2 * nchunk, GM_CONTRACT_WARPS * 32, smem, st>>>(C);
+    GM_LAUNCH_CHECK(h);
+    if (t->timing) {
+      GM_CUDA_TRY(cudaEventRecord(t->ev[1], st));
+      GM_CUDA_TRY(cudaEventSynchronize(t->ev[1]));
+      GM_CUDA_TRY(cudaEventElapsedTime(&ms, t->ev[0], t->ev[1]));
+      t->ms_contract += ms;
+    }
+    if (!per_particle) {
+      if (t->timing) GM_CUDA_TRY(cudaEventRecord(t->ev[0], st));
+      k_finalize<<<nt, GM_NANG_PAD, 0, st>>>(nchunk, G.ngroup, nmode, t->nang, t->part.as<double>(), t->scal_part.as<double>(),
+                                             d_out_phase + (size_t)t0 * 4 * t->nang, d_out_scal + (size_t)t0 * nmode * GM_NSCAL);
+      GM_LAUNCH_CHECK(h);
+      if (t->timing) {
+        GM_CUDA_TRY(cudaEventRecord(t->ev[1], st));
+        GM_CUDA_TRY(cudaEventSynchronize(t->ev[1]));
+        GM_CUDA_TRY(cudaEventElapsedTime(&ms, t->ev[0], t->ev[1]));
+        t->ms_finalize += ms;
+      }
+    }
+  }
+  t->last_stats[4] = (double)(h->launches - launches0);
+  return GM_OK;
+}
+
+static int fetch_stats(gm_table_t t) {
+  unsigned long long s[8];
+  GM_CUDA_TRY(cudaMemcpyAsync(s, t->stats.p, sizeof(s), cudaMemcpyDeviceToHost, t->h->stream));
+  GM_CUDA_TRY(cudaStreamSynchronize(t->h->stream));
+  for (int i = 0; i < 4; ++i) t->last_stats[i] = (double)s[i];
+  return GM_OK;
+}
+
+extern "C" int gm_table_run_dev(gm_table_t t, int ntask, const double* mz, const double* mrel, int nmode, const double* w_phase,
+                                const double* w_scal, int flags, double* out_scal, double* out_phase) {
+  GM_REQUIRE(t != nullptr, "table is NULL");
+  GM_REQUIRE(ntask > 0 && nmode >= 1 && nmode <= 32, "ntask / nmode out of range");
+  GM_REQUIRE(mz && mrel && w_phase && out_scal && out_phase, "NULL argument");
+  GM_REQUIRE(w_scal || nmode == 1, "w_scal is required when nmode > 1");
+  GM_CUDA_TRY(cudaSetDevice(t->h->device));
+  return table_run_core(t, ntask, mz, mrel, nmode, w_phase, w_scal, flags, out_scal, out_phase, nullptr, nullptr, false);
+}
+
+extern "C" int gm_table_run(gm_table_t t, int ntask, const double* mz, const double* mrel, int nmode, const double* w_phase,
+                            const double* w_scal, int flags, double* out_scal, double* out_phase) {
+  GM_REQUIRE(t != nullptr, "table is NULL");
+  GM_REQUIRE(ntask > 0 && nmode >= 1 && nmode <= 32, "ntask / nmode out of range");
+  GM_REQUIRE(mz && mrel && w_phase && out_scal && out_phase, "NULL argument");
+  GM_REQUIRE(w_scal || nmode == 1, "w_scal is required when nmode > 1");
+  gm_handle_t h = t->h;
+  GM_CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  int rc;
+  const size_t nw = (size_t)ntask * t->nx;
+  if ((rc = t->mz.ensure(sizeof(double2) * ntask)) || (rc = t->mrel.ensure(sizeof(double2) * ntask)) ||
+      (rc = t->wphase.ensure(sizeof(double) * nw)) || (rc = t->out_scal.ensure(sizeof(double) * (size_t)ntask * nmode * GM_NSCAL)) ||
+      (rc = t->out_phase.ensure(sizeof(double) * (size_t)ntask * 4 * t->nang)))
+    return rc;
+  if (w_scal && (rc = t->wscal.ensure(sizeof(double) * nw * nmode))) return rc;
+  GM_CUDA_TRY(cudaMemcpyAsync(t->mz.p, mz, sizeof(double2) * ntask, cudaMemcpyHostToDevice, st));
+  GM_CUDA_TRY(cudaMemcpyAsync(t->mrel.p, mrel, sizeof(double2) * ntask, cudaMemcpyHostToDevice, st));
+  GM_CUDA_TRY(cudaMemcpyAsync(t->wphase.p, w_phase, sizeof(double) * nw, cudaMemcpyHostToDevice, st));
+  if (w_scal) GM_CUDA_TRY(cudaMemcpyAsync(t->wscal.p, w_scal, sizeof(double) * nw * nmode, cudaMemcpyHostToDevice, st));
+  rc = table_run_core(t, ntask, t->mz.as<double>(), t->mrel.as<double>(), nmode, t->wphase.as<double>(),
+                      w_scal ? t->wscal.as<double>() : nullptr, flags, t->out_scal.as<double>(), t->out_phase.as<double>(), nullptr,
+                      nullptr, false);
+  if (rc) return rc;
+  GM_CUDA_TRY(cudaMemcpyAsync(out_scal, t->out_scal.p, sizeof(double) * (size_t)ntask * nmode * GM_NSCAL, cudaMemcpyDeviceToHost, st));
+  GM_CUDA_TRY(cudaMemcpyAsync(out_phase, t->out_phase.p, sizeof(double) * (size_t)ntask * 4 * t->nang, cudaMemcpyDeviceToHost, st));
+  return fetch_stats(t);
+}
+
+extern "C" int gm_table_particles(gm_table_t t, int ntask, const double* mz, const double* mrel, double* q, double* s12) {
+  GM_REQUIRE(t != nullptr, "table is NULL");
+  GM_REQUIRE(ntask > 0 && mz && mrel, "bad arguments");
+  gm_handle_t h = t->h;
+  GM_CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  int rc;
+  const size_t np = (size_t)ntask * t->nx;
+  if ((rc = t->mz.ensure(sizeof(double2) * ntask)) || (rc = t->mrel.ensure(sizeof(double2) * ntask)) ||
+      (rc = t->q.ensure(sizeof(double) * 6 * np)) || (rc = t->wphase.ensure(sizeof(double) * np)))
+    return rc;
+  if (s12 && (rc = t->s12.ensure(sizeof(double) * 4 * np * t->nang))) return rc;
+  GM_CUDA_TRY(cudaMemcpyAsync(t->mz.p, mz, sizeof(double2) * ntask, cudaMemcpyHostToDevice, st));
+  GM_CUDA_TRY(cudaMemcpyAsync(t->mrel.p, mrel, sizeof(double2) * ntask, cudaMemcpyHostToDevice, st));
+  GM_CUDA_TRY(cudaMemsetAsync(t->wphase.p, 0, sizeof(double) * np, st));
+  if ((rc = t->out_scal.ensure(sizeof(double) * (size_t)ntask * GM_NSCAL)) || (rc = t->out_phase.ensure(sizeof(double) * (size_t)ntask * 4 * t->nang)))
+    return rc;
+  rc = table_run_core(t, ntask, t->mz.as<double>(), t->mrel.as<double>(), 1, t->wphase.as<double>(), nullptr, 0,
+                      t->out_scal.as<double>(), t->out_phase.as<double>(), t->q.as<double>(), s12 ? t->s12.as<double>() : nullptr,
+                      s12 != nullptr);
+  if (rc) return rc;
+  if (q) GM_CUDA_TRY(cudaMemcpyAsync(q, t->q.p, sizeof(double) * 6 * np, cudaMemcpyDeviceToHost, st));
+  if (s12) GM_CUDA_TRY(cudaMemcpyAsync(s12, t->s12.p, sizeof(double) * 4 * np * t->nang, cudaMemcpyDeviceToHost, st));
+  return fetch_stats(t);
+}

@@ -1,0 +1,100 @@
+// gm_common.cuh -- shared host/device helpers for libgeosmie_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/geosmie_b200.h"
+
+// ------------------------------------------------------------------------------------------------ errors
+void gm_set_error(const char* fmt, ...);
+
+#define GM_CUDA_TRY(expr)                                                                       \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      gm_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return GM_ECUDA;                                                                          \
+    }                                                                                           \
+  } while (0)
+
+#define GM_REQUIRE(cond, msg)                                     \
+  do {                                                            \
+    if (!(cond)) {                                                \
+      gm_set_error("invalid argument: %s (%s)", msg, #cond);      \
+      return GM_EINVAL;                                           \
+    }                                                             \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------ device buffers
+// Grow-only device allocation; keeps repeated API calls free of cudaMalloc.
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return GM_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      gm_set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+      p = nullptr;
+      return GM_ENOMEM;
+    }
+    cap = want;
+    return GM_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct gm_handle_s {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  int64_t launches = 0;
+  // scratch for the per-particle API and GSF/bands
+  DevBuf ws[16];
+  size_t coef_budget_bytes = (size_t)2 << 30;  // coefficient staging buffer per gm_table_run batch
+};
+
+// ------------------------------------------------------------------------------------------------ table geometry
+// Layout constants shared by the coefficient kernel (producer) and the DMMA contraction kernel (consumer).
+constexpr int GM_GROUP = 32;          // particles per group = one warp of the coefficient kernel = DMMA N extent / 2
+constexpr int GM_NHALF = 2;           // the angle axis is split in two halves of GM_HALF_ANG angles
+constexpr int GM_HALF_ANG = 192;      // angles per CTA of the contraction kernel (12 warps x 16)
+constexpr int GM_NANG_PAD = GM_NHALF * GM_HALF_ANG;
+constexpr int GM_LAH = 194;           // doubles per table row per half (192 + 2 pad: row stride 388 = 4 mod 16 -> conflict-free A fragments)
+constexpr int GM_TROW = 2 * GM_LAH;   // p_n row then q_n row
+constexpr int GM_SB = 132;            // doubles per coefficient row: 64 (c+) + 64 (c-) + 4 pad (stride 4 mod 16 -> conflict-free B fragments)
+constexpr int GM_KSTEP = 4;           // DMMA k extent
+constexpr int GM_STAGE_DBL = GM_KSTEP * GM_TROW + GM_KSTEP * GM_SB;
+constexpr int GM_STAGES = 8;
+constexpr int GM_CONTRACT_WARPS = 12;
+
+// ------------------------------------------------------------------------------------------------ complex helpers
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+  return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ double2 crcp(double2 b) {
+  double inv = 1.0 / fma(b.x, b.x, b.y * b.y);
+  return make_double2(b.x * inv, -b.y * inv);
+}
+__device__ __forceinline__ double2 cdiv(double2 a, double2 b) {
+  double inv = 1.0 / fma(b.x, b.x, b.y * b.y);
+  return make_double2(fma(a.x, b.x, a.y * b.y) * inv, fma(a.y, b.x, -a.x * b.y) * inv);
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}

@@ -1,0 +1,254 @@
+// gm_gsf.cu -- generalized-spherical-function expansion of the six phase-matrix elements (north-star item 4).
+// Replaces one run of the Fortran program src/gsf/spher_expan.f per (bin, wavelength, RH) cell.
+//   host (once per call): Gauss-Legendre nodes/weights (GAUSS :520-579, N = ng, weights x2 as for IND1 = 0), the
+//     interpolation bracket of every node in the input angle grid (LINTERPOL :593-623) and the table of generalized
+//     spherical functions P^l_00, P^l_22, P^l_2-2, P^l_02 at the nodes (GENER :363-407, coefficients :293-303);
+//   device (one CTA per cell): interpolate the six elements to the nodes, weight, contract with the table
+//     (SPHER_EXPAN :304-347) in the Fortran accumulation order, normalise by AL1(0) (main :95-103).
+#include <math.h>
+
+#include "gm_common.cuh"
+
+#define GM_LAUNCH_CHECK(h)               \
+  do {                                   \
+    (h)->launches++;                     \
+    GM_CUDA_TRY(cudaGetLastError());     \
+  } while (0)
+
+namespace {
+
+// GAUSS(N, IND1=0, IND2=0, Z, W), spher_expan.f:520-579
+void gauss_nodes(int N, std::vector<double>& Z, std::vector<double>& W) {
+  Z.assign(N, 0.0);
+  W.assign(N, 0.0);
+  const double A = 1.0, B = 2.0, C = 3.0;
+  const int IND = N % 2;
+  const int K = N / 2 + IND;
+  const double F = (double)N;
+  for (int I = 1; I <= K; ++I) {
+    const int M = N + 1 - I;
+    double X = 0.0;
+    if (I == 1) X = A - B / ((F + A) * F);
+    if (I == 2) X = (Z[N - 1] - A) * 4.0 + Z[N - 1];
+    if (I == 3) X = (Z[N - 2] - Z[N - 1]) * 1.6 + Z[N - 2];
+    if (I > 3) X = (Z[M] - Z[M + 1]) * C + Z[M + 2];
+    if (I == K && IND == 1) X = 0.0;
+    int NITER = 0;
+    double CHECK = 1e-16;
+    double PA, PB, PC;
+    for (;;) {
+      PB = 1.0;
+      NITER++;
+      if (NITER > 100) CHECK = CHECK * 10.0;
+      PC = X;
+      double DJ = A;
+      for (int J = 2; J <= N; ++J) {
+        DJ = DJ + A;
+        PA = PB;
+        PB = PC;
+        PC = X * PB + (X * PB - PA) * (DJ - A) / DJ;
+      }
+      PA = A / ((PB - X * PC) * F);
+      PB = PA * PC * (A - X * X);
+      X = X - PB;
+      if (!(fabs(PB) > CHECK * fabs(X))) break;
+    }
+    Z[M - 1] = X;
+    W[M - 1] = PA * PA * (A - X * X);
+    W[M - 1] = B * W[M - 1];  // IND1 == 0
+    if (I == K && IND == 1) continue;
+    Z[I - 1] = -Z[M - 1];
+    W[I - 1] = W[M - 1];
+  }
+}
+
+// GENER(U, L1MAX) for all nodes: table G[4][node i][l] (l fastest), spher_expan.f:293-303 and :363-407
+void gsf_table(int ng, const std::vector<double>& X, std::vector<double>& G) {
+  const int L1MAX = ng;
+  std::vector<double> c1(L1MAX + 2), c2(L1MAX + 2), c3(L1MAX + 2), c4(L1MAX + 2), c5(L1MAX + 2), c6(L1MAX + 2), c7(L1MAX + 2),
+      c8(L1MAX + 2);
+  for (int L1 = 3; L1 <= L1MAX; ++L1) {
+    const int L = L1 - 1;
+    c1[L1] = 1.0 / (double)(L + 1);
+    c2[L1] = (double)(2 * L + 1);
+    c3[L1] = 1.0 / sqrt((double)((L + 1) * (L + 1) - 4));
+    c4[L1] = sqrt((double)(L * L - 4));
+    c5[L1] = 1.0 / ((double)L * (double)((L + 1) * (L + 1) - 4));
+    c6[L1] = (double)(2 * L + 1) * (double)(L * (L + 1));
+    c7[L1] = (double)((2 * L + 1) * 4);
+    c8[L1] = (double)(L + 1) * (double)(L * L - 4);
+  }
+  const double D6 = 0.25 * sqrt(6.0);
+  G.assign((size_t)4 * ng * ng, 0.0);
+  std::vector<double> P1(L1MAX + 2), P2(L1MAX + 2), P3(L1MAX + 2), P4(L1MAX + 2);
+  for (int i = 0; i < ng; ++i) {
+    const double U = X[i];
+    const double DUP = 1.0 + U, DUM = 1.0 - U, DU = U * U;
+    P1[1] = 1.0; P1[2] = U; P1[3] = 0.5 * (3.0 * DU - 1.0);
+    P2[1] = 0.0; P2[2] = 0.0; P2[3] = 0.25 * DUP * DUP;
+    P3[1] = 0.0; P3[2] = 0.0; P3[3] = 0.25 * DUM * DUM;
+    P4[1] = 0.0; P4[2] = 0.0; P4[3] = D6 * (DU - 1.0);
+    const int LMAX = L1MAX - 1;
+    for (int L1 = 3; L1 <= LMAX; ++L1) {
+      const double CU1 = c2[L1] * U, CU2 = c6[L1] * U;
+      const int L2 = L1 + 1, L3 = L1 - 1;
+      const double DL = (double)L3;
+      P1[L2] = c1[L1] * (CU1 * P1[L1] - DL * P1[L3]);
+      P2[L2] = c5[L1] * ((CU2 - c7[L1]) * P2[L1] - c8[L1] * P2[L3]);
+      P3[L2] = c5[L1] * ((CU2 + c7[L1]) * P3[L1] - c8[L1] * P3[L3]);
+      P4[L2] = c3[L1] * (CU1 * P4[L1] - c4[L1] * P4[L3]);
+    }
+    for (int l = 0; l < ng; ++l) {
+      G[((size_t)0 * ng + i) * ng + l] = (l + 1 <= L1MAX && (l < 3 || true)) ? P1[l + 1] : 0.0;
+      G[((size_t)1 * ng + i) * ng + l] = P2[l + 1];
+      G[((size_t)2 * ng + i) * ng + l] = P3[l + 1];
+      G[((size_t)3 * ng + i) * ng + l] = P4[l + 1];
+    }
+  }
+}
+
+struct GsfNode {
+  double dxinv_num;  // X - XX(I-1)   (radians)
+  double dx;         // XX(I) - XX(I-1)
+  double w;          // Gauss weight
+  int i0, i1;        // indices of YY(I-1), YY(I) (0-based)
+};
+
+__global__ void __launch_bounds__(256) k_gsf(int nang, int ng, const double* __restrict__ F, const GsfNode* __restrict__ nodes,
+                                             const double* __restrict__ G, double* __restrict__ coef, double* __restrict__ cnorm,
+                                             int quantize10) {
+  extern __shared__ double sm[];
+  double* f = sm;                 // [6][nang]
+  double* ff = sm + 6 * nang;     // [6][ng]: FF11, FP, FM, FF44, FF12, FF34
+  double* res = ff + 6 * ng;      // [6][ng]
+  const int cell = blockIdx.x;
+  const double* Fc = F + (size_t)cell * 6 * nang;
+  for (int k = threadIdx.x; k < 6 * nang; k += blockDim.x) f[k] = Fc[k];
+  __syncthreads();
+  for (int i = threadIdx.x; i < ng; i += blockDim.x) {
+    const GsfNode nd = nodes[i];
+    double v[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const double y0 = f[k * nang + nd.i0], y1 = f[k * nang + nd.i1];
+      // LINTERPOL: Y = (YY(I)-YY(I-1))/(XX(I)-XX(I-1))*(X-XX(I-1))+YY(I-1)   (no FMA contraction)
+      v[k] = __dadd_rn(__dmul_rn(__ddiv_rn(__dsub_rn(y1, y0), nd.dx), nd.dxinv_num), y0);
+      v[k] = __dmul_rn(v[k], nd.w);                        // FFxx = Fxx(I)*WI, :316-321
+    }
+    // input order F11,F22,F33,F44,F12,F34
+    ff[0 * ng + i] = v[0];
+    ff[1 * ng + i] = __dadd_rn(v[1], v[2]);               // FP = FF22+FF33
+    ff[2 * ng + i] = __dsub_rn(v[1], v[2]);               // FM = FF22-FF33
+    ff[3 * ng + i] = v[3];
+    ff[4 * ng + i] = v[4];
+    ff[5 * ng + i] = v[5];
+  }
+  __syncthreads();
+  // accumulation over the nodes in the Fortran order (DO 300 I / DO 260 L1), one thread per (series, l)
+  for (int o = threadIdx.x; o < 6 * ng; o += blockDim.x) {
+    const int s = o / ng, l = o % ng;
+    // series: 0 AL1 (FF11,P1) 1 AL2acc (FP,P2) 2 AL3acc (FM,P3) 3 AL4 (FF44,P1) 4 BET1 (FF12,P4) 5 BET2 (FF34,P4)
+    const int gsel = (s == 0 || s == 3) ? 0 : (s == 1 ? 1 : (s == 2 ? 2 : 3));
+    const double* g = G + (size_t)gsel * ng * ng + l;
+    const double* w = ff + s * ng;
+    double acc = 0.0;
+    for (int i = 0; i < ng; ++i) acc = __dadd_rn(acc, __dmul_rn(w[i], g[(size_t)i * ng]));
+    res[o] = acc;
+  }
+  __syncthreads();
+  // DO 350: scaling by (l + 1/2) and the AL2/AL3 recombination, then CNORM = 1/AL1(1)
+  const double cn = 1.0 / (res[0] * 0.5);
+  for (int l = threadIdx.x; l < ng; l += blockDim.x) {
+    const double CL = (double)l + 0.5;
+    const double al1 = res[0 * ng + l] * CL;
+    const double a2 = res[1 * ng + l] * CL * 0.5;
+    const double a3 = res[2 * ng + l] * CL * 0.5;
+    double o[6] = {al1, a2 + a3, a2 - a3, res[3 * ng + l] * CL, res[4 * ng + l] * CL, res[5 * ng + l] * CL};
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      double v = o[k] * cn;
+      if (quantize10) v = rint(v * 1e10) / 1e10;
+      coef[((size_t)cell * 6 + k) * ng + l] = v;
+    }
+  }
+  if (threadIdx.x == 0 && cnorm) cnorm[cell] = cn;
+}
+
+int gsf_core(gm_handle_t h, int ncell, int nang, const double* h_ang_deg, const double* d_F, int ng, double* d_coef,
+             double* d_cnorm, int quantize10) {
+  GM_REQUIRE(ng >= 3 && ng <= 2048, "ng out of range");
+  GM_REQUIRE(nang >= 2 && nang <= 1000, "nang out of range (NANG_MAX = 1000, params.h:1)");
+  cudaStream_t st = h->stream;
+  std::vector<double> X, W, G;
+  gauss_nodes(ng, X, W);
+  gsf_table(ng, X, G);
+  // angles in radians: angl(i) = angl(i)*D2R, D2R = PI/180 with PI = DACOS(-1) (params.h:3-4, spher_expan.f:260-263)
+  const double PI = acos(-1.0), D2R = PI / 180.0;
+  std::vector<double> XX(nang);
+  for (int i = 0; i < nang; ++i) XX[i] = h_ang_deg[i] * D2R;
+  std::vector<GsfNode> nodes(ng);
+  for (int i = 0; i < ng; ++i) {
+    const double x = acos(X[i]);
+    int I;  // 1-based index of the upper bracket as in LINTERPOL
+    if (x < XX[0]) {
+      // Y = (YY(1)-YY(2))/(XX(1)-XX(2))*(X-XX(1))+YY(1)
+      nodes[i].i0 = 0; nodes[i].i1 = 1;
+      // rewrite in the generic form with (y1 - y0)/(dx) * num + y0: (YY(1)-YY(2))/(XX(1)-XX(2)) = (y1 - y0)/(XX(2)-XX(1)) up to rounding
+      nodes[i].dx = XX[1] - XX[0];
+      nodes[i].dxinv_num = x - XX[0];
+    } else if (x > XX[nang - 1]) {
+      nodes[i].i0 = nang - 2; nodes[i].i1 = nang - 1;
+      nodes[i].dx = XX[nang - 1] - XX[nang - 2];
+      // Y = slope*(X-XX(NN)) + YY(NN) == slope*(X - XX(NN-1)) + YY(NN-1) up to rounding
+      nodes[i].dxinv_num = x - XX[nang - 2];
+    } else {
+      for (I = 2; I <= nang; ++I)
+        if (XX[I - 1] > x) break;
+      if (I > nang) I = nang;  // X == XX(NN): the Fortran loop leaves I = NN+1; guard against reading past the end
+      nodes[i].i0 = I - 2; nodes[i].i1 = I - 1;
+      nodes[i].dx = XX[I - 1] - XX[I - 2];
+      nodes[i].dxinv_num = x - XX[I - 2];
+    }
+    nodes[i].w = W[i];
+  }
+  int rc;
+  if ((rc = h->ws[0].ensure(sizeof(GsfNode) * ng)) || (rc = h->ws[1].ensure(sizeof(double) * G.size()))) return rc;
+  GM_CUDA_TRY(cudaMemcpyAsync(h->ws[0].p, nodes.data(), sizeof(GsfNode) * ng, cudaMemcpyHostToDevice, st));
+  GM_CUDA_TRY(cudaMemcpyAsync(h->ws[1].p, G.data(), sizeof(double) * G.size(), cudaMemcpyHostToDevice, st));
+  const size_t smem = sizeof(double) * (6 * (size_t)nang + 12 * (size_t)ng);
+  GM_CUDA_TRY(cudaFuncSetAttribute(k_gsf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_gsf<<<ncell, 256, smem, st>>>(nang, ng, d_F, h->ws[0].as<GsfNode>(), h->ws[1].as<double>(), d_coef, d_cnorm, quantize10);
+  GM_LAUNCH_CHECK(h);
+  GM_CUDA_TRY(cudaStreamSynchronize(st));  // nodes/G are stack-owned
+  return GM_OK;
+}
+
+}  // namespace
+
+extern "C" int gm_gsf_expand_dev(gm_handle_t h, int ncell, int nang, const double* ang_deg, const double* F, int ng, double* coef,
+                                 double* cnorm, int quantize10) {
+  GM_REQUIRE(h && ang_deg && F && coef, "NULL argument");
+  GM_REQUIRE(ncell > 0, "ncell must be > 0");
+  GM_CUDA_TRY(cudaSetDevice(h->device));
+  return gsf_core(h, ncell, nang, ang_deg, F, ng, coef, cnorm, quantize10);
+}
+
+extern "C" int gm_gsf_expand(gm_handle_t h, int ncell, int nang, const double* ang_deg, const double* F, int ng, double* coef,
+                             double* cnorm, int quantize10) {
+  GM_REQUIRE(h && ang_deg && F && coef, "NULL argument");
+  GM_REQUIRE(ncell > 0, "ncell must be > 0");
+  GM_CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  int rc;
+  const size_t nf = (size_t)ncell * 6 * nang, nc = (size_t)ncell * 6 * ng;
+  if ((rc = h->ws[2].ensure(sizeof(double) * nf)) || (rc = h->ws[3].ensure(sizeof(double) * nc)) ||
+      (rc = h->ws[4].ensure(sizeof(double) * ncell)))
+    return rc;
+  GM_CUDA_TRY(cudaMemcpyAsync(h->ws[2].p, F, sizeof(double) * nf, cudaMemcpyHostToDevice, st));
+  rc = gsf_core(h, ncell, nang, ang_deg, h->ws[2].as<double>(), ng, h->ws[3].as<double>(), h->ws[4].as<double>(), quantize10);
+  if (rc) return rc;
+  GM_CUDA_TRY(cudaMemcpyAsync(coef, h->ws[3].p, sizeof(double) * nc, cudaMemcpyDeviceToHost, st));
+  if (cnorm) GM_CUDA_TRY(cudaMemcpyAsync(cnorm, h->ws[4].p, sizeof(double) * ncell, cudaMemcpyDeviceToHost, st));
+  GM_CUDA_TRY(cudaStreamSynchronize(st));
+  return GM_OK;
+}

@@ -1,0 +1,144 @@
+/*
+ * geosmie_b200.h -- C ABI of libgeosmie_b200.so (hand-written sm_100a CUDA; no torch types, no exceptions).
+ *
+ * This is the drop-in boundary for the GEOSmie Mie lookup-table hot path.  Every entry point names the
+ * reference interface it replaces (paths relative to the GEOS-ESM/GEOSmie tree).  Conventions:
+ *   - all floating point is IEEE double; complex numbers are (re, im) pairs of doubles; m = n + i k, k > 0 absorbing;
+ *   - all arrays are caller-owned, C-contiguous; the library never frees or retains caller memory;
+ *   - functions return 0 on success or a negative GM_E* code; gm_last_error() gives a thread-local message;
+ *   - `*_dev` variants take DEVICE pointers and enqueue asynchronously on the handle's stream (gm_set_stream),
+ *     the plain variants take HOST pointers, copy in/out and synchronise before returning;
+ *   - one handle per GPU, a handle must not be used from two threads at once.
+ */
+#ifndef GEOSMIE_B200_H
+#define GEOSMIE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GM_OK 0
+#define GM_EINVAL (-1)
+#define GM_ECUDA (-2)
+#define GM_ENOMEM (-3)
+
+/* number of raw size-distribution sums returned per (task, mode) by gm_table_run, see GM_S_* below */
+#define GM_NSCAL 11
+#define GM_S_W 0      /* sum w                      (integratePSD `num`, dointegration.py:1104) */
+#define GM_S_X2W 1    /* sum x^2 w                  (rarr2, :1105; r = x*lam/2pi applied by the caller) */
+#define GM_S_X3W 2    /* sum x^3 w                  (rarr3, :1106) */
+#define GM_S_X4W 3    /* sum x^4 w                  (rarr4, :1107) */
+#define GM_S_QEXT 4   /* sum qext x^2 w             (:1188-1190 'dumix', area weighting :1111-1112) */
+#define GM_S_QSCA 5   /* sum qsca x^2 w */
+#define GM_S_QABS 6   /* sum qabs x^2 w */
+#define GM_S_QB 7     /* sum qb   x^2 w             (:1133-1145) */
+#define GM_S_G 8      /* sum g qsca x^2 w           (thisweight *= qsca aliasing quirk, :1157) */
+#define GM_S_CSCA 9   /* sum qsca^2 x^4 w           (csca = qsca pi r^2 with the (area*qsca) weight) */
+#define GM_S_CEXT 10  /* sum qext qsca x^4 w */
+
+/* flags for gm_table_run */
+#define GM_F_ELIDE_ZERO_WEIGHT 1 /* skip particles whose weights are all exactly 0 (result-neutral) */
+
+typedef struct gm_handle_s* gm_handle_t;
+typedef struct gm_table_s* gm_table_t;
+
+/* ---- lifetime ---------------------------------------------------------------------------------------------------- */
+int gm_version(void);
+const char* gm_last_error(void);
+int gm_init(int device, gm_handle_t* out);
+int gm_destroy(gm_handle_t h);
+/* `cuda_stream` is a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); NULL = default stream */
+int gm_set_stream(gm_handle_t h, void* cuda_stream);
+int gm_sync(gm_handle_t h);
+/* kernels launched by this handle since gm_init (for bench.py's gpu_launches) */
+int64_t gm_launch_count(gm_handle_t h);
+
+/* ---- B1/B2: per-particle Mie ----------------------------------------------------------------------------------------
+ * Replaces pymiecoated mie_coeffs(params) + mie_props + mie_S12 (mie_coeffs.py:36-73, :132-180, :183-251;
+ * mie_props.py:28-70, :119-150) and the batch loop MultipleMie.calculateS12SizeRange (mie_coated.py:61-89).
+ *   n         particles
+ *   x[n]      size parameter used in the homogeneous formulas (the reference passes y when it falls back to
+ *             single_mie_coeff, mie_coeffs.py:66-69 -- the Python wrapper performs that dispatch)
+ *   xcore[n]  NULL for homogeneous spheres; else core size parameter (then x[] is the shell size parameter y)
+ *   mz[n][2]  sqrt(eps*mu), mrel[n][2] sqrt(eps/mu)  (mie_coeffs.py:96-97); coated: m1 = sqrt(eps1) in mz, m2 = sqrt(eps2) in mrel
+ *   mat_stride 0: one material broadcast to all particles, 1: per-particle material
+ *   nmax[n]   number of terms, computed by the caller with the reference expression (mie_coeffs.py:99)
+ *   bes_off/ajv/ayv  optional caller-supplied J_{k+1.5}(x), Y_{k+1.5}(x), k = 0..nmax-1, particle i at bes_off[i]
+ *             (the reference's ajv/ayv inputs, mie_coated.py:260-263); NULL = computed on the device
+ *   nang,u    cosines of the scattering angles (may be 0 / NULL)
+ * outputs
+ *   q[n][6]   qext,qsca,qabs,qb,asy,qratio  (mie_props_raw return order, mie_props.py:70)
+ *   s12[n][nang][4]  Re S1, Im S1, Re S2, Im S2 (nullable)
+ *   ab[sum nmax][4]  Re a_n, Im a_n, Re b_n, Im b_n concatenated per particle (nullable)
+ */
+int gm_mie_eval(gm_handle_t h, int n, const double* x, const double* xcore, const double* mz, const double* mrel,
+                int mat_stride, const int32_t* nmax, const int64_t* bes_off, const double* ajv, const double* ayv,
+                int nang, const double* u, double* q, double* s12, double* ab);
+
+/* ---- B3: fused table cells ------------------------------------------------------------------------------------------
+ * A table object holds the per-bin constants of dointegration.fun's bin loop (dointegration.py:787-798):
+ * the size-parameter grid, nmax, the Riccati-Bessel tables psi_n(x), chi_n(x) (replaces
+ * MultipleMie.preCalculateBessel, mie_coated.py:153-158) and the pi_n/tau_n angle table (replaces
+ * preCalculatePT, mie_coated.py:160-179).
+ */
+int gm_table_create(gm_handle_t h, int nx, const double* x, const int32_t* nmax, int nang, const double* cos_theta,
+                    gm_table_t* out);
+int gm_table_destroy(gm_table_t t);
+int gm_table_nx(gm_table_t t);
+int gm_table_nang(gm_table_t t);
+/* optional validation mode: replace the device-computed Riccati-Bessel tables by caller-supplied
+ * J_{k+0.5}(x_i), Y_{k+0.5}(x_i), k = 0..nmax_i (note: nmax_i + 1 values per particle, particle i at off[i]) */
+int gm_table_set_bessel(gm_table_t t, const int64_t* off, const double* jv_half, const double* yv_half);
+
+/*
+ * gm_table_run: for each task (one complex refractive index + one weight vector over the bin's x grid) evaluate
+ * Mie at every x, form the Mueller elements at every angle and reduce over the size distribution.
+ * Replaces rawMie + calculateScatVals + the reductions of integratePSD (dointegration.py:1211-1254, :1044-1050,
+ * :1104-1107, :1164-1166, :1188-1190); the caller combines the raw sums exactly like integratePSD does.
+ *   mz/mrel [ntask][2]          as in gm_mie_eval (mu = 1: both sqrt(eps))
+ *   w_phase [ntask][nx]         number weights for the phase-matrix sums
+ *   w_scal  [ntask][nmode][nx]  number weights for the scalar sums (NULL: nmode must be 1 and w_phase is used)
+ *   out_scal [ntask][nmode][GM_NSCAL]
+ *   out_phase [ntask][4][nang]  sum_x w P(x,theta) for P11(=P22), P12, P33(=P44), P34
+ * Deterministic: fixed reduction order, bitwise identical results run to run.
+ */
+int gm_table_run(gm_table_t t, int ntask, const double* mz, const double* mrel, int nmode, const double* w_phase,
+                 const double* w_scal, int flags, double* out_scal, double* out_phase);
+int gm_table_run_dev(gm_table_t t, int ntask, const double* mz, const double* mrel, int nmode, const double* w_phase,
+                     const double* w_scal, int flags, double* out_scal, double* out_phase);
+/* per-particle outputs through the table (DMMA) path: q [ntask][nx][6], s12 [ntask][nx][nang][4] (host pointers) */
+int gm_table_particles(gm_table_t t, int ntask, const double* mz, const double* mrel, double* q, double* s12);
+/* statistics of the last gm_table_run*: [0] particle evaluations, [1] sum of nmax over evaluated particles,
+ * [2] sum of nmx, [3] executed DMMA k4-steps x 32 particles (padded work), [4] kernels launched */
+int gm_table_last_stats(gm_table_t t, double stats[8]);
+/* CUDA-event time (ms) of the contraction kernel launches of the last run (0 if timing disabled) */
+int gm_table_set_timing(gm_table_t t, int enable);
+int gm_table_last_kernel_ms(gm_table_t t, double* coeff_ms, double* contract_ms, double* finalize_ms);
+
+/* ---- B4: generalized-spherical-function expansion ---------------------------------------------------------------------
+ * Replaces one run of ./spher_expan.x per cell (src/gsf/spher_expan.f main :1-110, one_calc :120-180,
+ * GAUSS :520-579, LINTERPOL :593-623, SPHER_EXPAN :269-358, GENER :363-407) as spawned by convertncdf.convertData
+ * (src/gsf/convertncdf.py:173-189).
+ *   F [ncell][6][nang]   order F11,F22,F33,F44,F12,F34 (convertncdf.py:177) at angles ang_deg[nang] (ascending)
+ *   coef [ncell][6][ng]  AL1,AL2,AL3,AL4,BET1,BET2 divided by AL1(0) (spher_expan.f:95-103); cnorm[ncell] = 1/AL1(0)
+ *   quantize10           round to 10 decimals like the Fortran '(X,I5,6F17.10)' output (:96,:104)
+ */
+int gm_gsf_expand(gm_handle_t h, int ncell, int nang, const double* ang_deg, const double* F, int ng, double* coef,
+                  double* cnorm, int quantize10);
+int gm_gsf_expand_dev(gm_handle_t h, int ncell, int nang, const double* ang_deg, const double* F, int ng, double* coef,
+                      double* cnorm, int quantize10);
+
+/* ---- B5: band averaging ----------------------------------------------------------------------------------------------
+ * Replaces bandaverage.doAverage (src/geosmie/bandaverage.py:18-50) over all (variable, bin, rh) columns.
+ *   v [ncol][nlam] at wavelengths lam[nlam] (metres, ascending); bands lo/hi [nband] in cm^-1 (use_wavenum=1) or metres
+ *   out [ncol][nband]
+ */
+int gm_band_average(gm_handle_t h, int ncol, int nlam, const double* lam, const double* v, int nband, const double* lo,
+                    const double* hi, int use_wavenum, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEOSMIE_B200_H */
