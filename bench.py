@@ -1,0 +1,327 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the GEOSmie Mie lookup-table hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): the sulfate table optics_SU -- su.json's lognormal bin on its 4459-point size grid
+x 61 wavelengths x 36 RH = 2196 cells = 9,791,964 Mie particle-evaluations per step (371 angles each), evaluated DENSE
+(zero-weight particles included, i.e. reference-equivalent work), followed by the GSF moment expansion of all cells.
+Refractive indices are the OPAC sulfate / HITRAN water values recorded in tests/golden/hostlogic.npz.
+
+One "step" = one pass of the hot path over that batch:
+  value  particle-evals/s with inputs (m, weights) resident in HBM (device-pointer C ABI, CUDA-event timed);
+  e2e    the same through the host-buffer C ABI (pinned host inputs -> H2D -> kernels -> D2H inside the timed region);
+  roofline   FP64 tensor (DMMA) roofline of the dominant kernel k_contract, duration from CUDA events recorded around
+             each of its launches on the launching stream inside the timed steps;
+  cpu_baseline   the CPU oracle port (oracle/mie_oracle.c, OpenMP) on a bounded sample of the same cells.
+With --gpus N (torchrun) every rank evaluates its own 2196-cell shard of an N-times larger grid (weak scaling) and the
+reduced sums are gathered to rank 0 with NCCL inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "mie_particle_evals_per_sec"
+UNIT = "particle-evals/s"
+NANG = 371
+FP64_PEAK_TFLOPS = 37.1   # measured on this pool's B200 with tools/fp64_peak.cu (DMMA m8n8k4), profiles/r01_fp64_peak.json
+
+RH36 = [0.00, 0.05, 0.10, 0.15, 0.20, 0.25, 0.30, 0.35, 0.40, 0.45, 0.50, 0.55, 0.60, 0.65, 0.70, 0.75, 0.80, 0.81, 0.82, 0.83,
+        0.84, 0.85, 0.86, 0.87, 0.88, 0.89, 0.90, 0.91, 0.92, 0.93, 0.94, 0.95, 0.96, 0.97, 0.98, 0.99]
+SU_PARAMS = {
+    "rhop0": 1700.0, "rh": RH36,
+    "rhDep": {"type": "simple", "params": {"gf": [1.00, 1.04, 1.08, 1.12, 1.16, 1.20, 1.23, 1.27, 1.31, 1.35, 1.39, 1.43, 1.46,
+                                                  1.50, 1.54, 1.59, 1.64, 1.65, 1.66, 1.67, 1.68, 1.69, 1.71, 1.72, 1.74, 1.75,
+                                                  1.77, 1.79, 1.82, 1.84, 1.87, 1.91, 1.94, 1.99, 2.05, 2.16]}},
+    "psd": {"type": "lognorm", "params": {"r0": [[0.0695e-6]], "rmin0": [[0.005e-6]], "rmax0": [[0.3e-6]], "sigma": [[2.03]],
+                                          "numperdec": [1000], "fracs": [[1.0]]}},
+}
+
+
+def build_su_plan():
+    """Host inputs of the SU table exactly as dointegration.fun derives them (grid, m(lambda, RH), number weights)."""
+    from scipy.interpolate import interp1d
+    from geosmie_b200 import dointegration as DI
+    g = np.load(os.path.join(ROOT, "tests", "golden", "hostlogic.npz"))
+    ml, water = g["su__mlist"], g["su__water"]
+    lambarr = ml[0]
+    part_m = [(interp1d(ml[0], ml[1]), interp1d(ml[0], ml[2]))]
+    water_m = (interp1d(water[0], water[1]), interp1d(water[0], water[2]))
+    params = json.loads(json.dumps(SU_PARAMS))
+    plan = DI.BinPlan(params, 0, lambarr, params["rh"], part_m, water_m)
+    return plan
+
+
+def flop_model(nmax, nmx_sum, ncell_factor=1):
+    """Algorithmic FP64 flop of one pass.  `contract`: what the S+/S- formulation of k_contract needs -- 4 FMA per
+    (particle, n, angle) + 8 FMA per (particle, angle) for the weighted Mueller products;  `survey`: the
+    SURVEY 8d model F(p) = nmax (16 N_ang + 94) + 14 nmx + 22 N_ang (four separate complex dot products)."""
+    snm = float(np.sum(nmax)) * ncell_factor
+    npart = float(len(nmax)) * ncell_factor
+    contract = snm * 8.0 * NANG + npart * 16.0 * NANG
+    survey = snm * (16.0 * NANG + 94.0) + 14.0 * nmx_sum + npart * 22.0 * NANG
+    return contract, survey
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = max(mx, float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        # under-load samples: the upper half of the SM clock readings
+        sm_sorted = sorted(sm)
+        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_baseline(plan, seconds=12.0, threads=None):
+    """Oracle port timed on the host cores on a bounded sample of SU cells (every cell costs the same: the grid is
+    shared, only m changes).  Returns the cpu_baseline dict."""
+    from oracle import mie_oracle as mo
+    threads = threads or len(os.sched_getaffinity(0))
+    cost = np.cos(np.radians(_angles()))
+    t0 = time.time()
+    sr = mo.SizeRange(plan.xx, cost)       # scipy Bessel pre-computation, once per bin like the reference
+    t_pre = time.time() - t0
+    ncell = len(plan.cells)
+    order = np.random.default_rng(0).permutation(ncell)
+    done, t_run = 0, 0.0
+    for ci in order:
+        m = plan.m[ci, 0]
+        t1 = time.time()
+        q, _, mu = sr.run(float(m.real), float(m.imag), want_mueller=True, nthreads=threads)
+        mo.raw_sums(plan.xx, q, mu, plan.w[ci, 0])
+        t_run += time.time() - t1
+        done += 1
+        if t_run > seconds:
+            break
+    evals = done * plan.xx.size
+    return {"value": evals / t_run, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d of %d SU cells x %d particles x %d angles (oracle/mie_oracle.c + OpenMP, %.1f s; one-off scipy Bessel "
+                      "pre-computation %.1f s not included)" % (done, ncell, plan.xx.size, NANG, t_run, t_pre)}, t_run
+
+
+def _angles():
+    return np.concatenate([np.linspace(0., 1., 100, endpoint=False), np.linspace(1., 10., 100, endpoint=False),
+                           np.linspace(10., 180., 171, endpoint=True)])
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  The reference is Python + numba and cannot
+    travel to the GPU box; its algorithm is timed through the oracle port (plain C + OpenMP on all host threads --
+    faster than the reference's own numba loops) on a bounded sample of the same workload per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    plan = build_su_plan()
+    vals = []
+    for s in range(args.warmup + args.steps):
+        cb, t = cpu_baseline(plan, seconds=4.0)
+        if s >= args.warmup:
+            vals.append((cb, t))
+    v = float(np.mean([c["value"] for c, _ in vals]))
+    cb = vals[-1][0]
+    cb["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean([t for _, t in vals])), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "su.json parameters, OPAC sulfate + HITRAN water indices",
+            "config": {"workload": "optics_SU dense: 4459 x (61 lambda x 36 RH) cells x 371 angles (bounded sample per step)"},
+            "cpu_baseline": cb, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--elide", action="store_true", help="also report the zero-weight-elided rate (extra, not the headline)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    from geosmie_b200 import _lib
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as td
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        td.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    plan = build_su_plan()
+    ang = _angles()
+    cost = np.cos(np.radians(ang))
+    ncell, nx = len(plan.cells), plan.xx.size
+    h = _lib.Handle.get(local)
+    stream = torch.cuda.current_stream()
+    h.set_stream(stream.cuda_stream)
+    table = _lib.Table(plan.xx, plan.nmax, cost, h)
+    table.set_timing(True)
+
+    mz_np, wp_np, ws_np, tpc = plan.tasks()
+    assert tpc == 1
+    # pinned host inputs (e2e) and device-resident copies (value)
+    mz_h = torch.from_numpy(np.ascontiguousarray(mz_np).view(np.float64).reshape(ncell, 2).copy()).pin_memory()
+    w_h = torch.from_numpy(np.ascontiguousarray(wp_np)).pin_memory()
+    mz_d, w_d = mz_h.to(dev), w_h.to(dev)
+    scal_d = torch.empty((ncell, 1, _lib.GM_NSCAL), dtype=torch.float64, device=dev)
+    phase_d = torch.empty((ncell, 4, NANG), dtype=torch.float64, device=dev)
+    coef_d = torch.empty((ncell, 6, 129), dtype=torch.float64, device=dev)
+    cn_d = torch.empty((ncell,), dtype=torch.float64, device=dev)
+    scal_h = torch.empty((ncell, 1, _lib.GM_NSCAL), dtype=torch.float64).pin_memory()
+    phase_h = torch.empty((ncell, 4, NANG), dtype=torch.float64).pin_memory()
+    coef_h = torch.empty((ncell, 6, 129), dtype=torch.float64).pin_memory()
+    gather_buf = None
+    if world > 1:
+        width = _lib.GM_NSCAL + 4 * NANG + 6 * 129
+        packed = torch.empty((ncell, width), dtype=torch.float64, device=dev)
+        gather_buf = [torch.empty_like(packed) for _ in range(world)] if rank == 0 else None
+
+    def step_device():
+        table.run_dev(ncell, mz_d.data_ptr(), mz_d.data_ptr(), 1, w_d.data_ptr(), 0, scal_d.data_ptr(), phase_d.data_ptr(), elide=False)
+        h.gsf_expand_phase4_dev(ang, ncell, phase_d.data_ptr(), coef_d.data_ptr(), cn_d.data_ptr())
+        if world > 1:
+            torch.cat([scal_d.reshape(ncell, -1), phase_d.reshape(ncell, -1), coef_d.reshape(ncell, -1)], dim=1, out=packed)
+            td.gather(packed, gather_buf, dst=0)
+
+    def step_e2e():
+        # the user-facing call with HOST buffers: H2D of this step's inputs, kernels, D2H of the results
+        mzd = mz_h.to(dev, non_blocking=True)
+        wd = w_h.to(dev, non_blocking=True)
+        table.run_dev(ncell, mzd.data_ptr(), mzd.data_ptr(), 1, wd.data_ptr(), 0, scal_d.data_ptr(), phase_d.data_ptr(), elide=False)
+        h.gsf_expand_phase4_dev(ang, ncell, phase_d.data_ptr(), coef_d.data_ptr(), cn_d.data_ptr())
+        scal_h.copy_(scal_d, non_blocking=True)
+        phase_h.copy_(phase_d, non_blocking=True)
+        coef_h.copy_(coef_d, non_blocking=True)
+        if world > 1:
+            torch.cat([scal_d.reshape(ncell, -1), phase_d.reshape(ncell, -1), coef_d.reshape(ncell, -1)], dim=1, out=packed)
+            td.gather(packed, gather_buf, dst=0)
+
+    def barrier():
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            td.all_reduce(t, op=td.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    launches0 = h.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    ms_dev = timed(step_device, args.steps)
+    launches = (h.launch_count() - launches0) // args.steps
+    kms = table.last_kernel_ms()            # CUDA events around the launches of the LAST timed step
+    stats = table.last_stats()
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    total_evals = float(ncell) * nx * world
+    value = total_evals / (ms_dev * 1e-3)
+    e2e = total_evals / (ms_e2e * 1e-3)
+    contract_flop, survey_flop = flop_model(plan.nmax, stats["sum_nmx"], ncell)
+    ach = contract_flop / (kms["contract"] * 1e-3) / 1e12 if kms["contract"] > 0 else None
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "su.json parameters; OPAC sulfate + HITRAN water refractive indices (tests/golden/hostlogic.npz)",
+        "config": {"workload": "optics_SU dense table build: 1 bin x 4459 sizes x 61 lambda x 36 RH = 2196 cells, 371 angles, "
+                               "then 129 GSF moments x 6 per cell", "cells_per_gpu": ncell, "nx": nx, "nang": NANG,
+                   "l2_policy": "inputs larger than L2 per step: 78 MB weights + 2.9 GB coefficient stream re-written every step",
+                   "parallelism": "cells sharded, %d rank(s), NCCL gather to rank 0" % world},
+        "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": int(mz_h.numel() * 8 + w_h.numel() * 8),
+                "d2h_bytes_per_step": int(scal_h.numel() * 8 + phase_h.numel() * 8 + coef_h.numel() * 8)},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "kernel": "k_contract<false> (FP64 DMMA m8n8k4)", "achieved": ach, "peak": FP64_PEAK_TFLOPS,
+                     "unit": "TFLOP/s", "frac": (ach / FP64_PEAK_TFLOPS) if ach else None, "traffic": None,
+                     "peak_source": "measured on this pool: tools/fp64_peak.cu DMMA burst 37.1 TFLOP/s (MEASURED_PEAKS.json has "
+                                    "no FP64 entry; nominal 37 TFLOP/s)",
+                     "flop_per_launch_set": contract_flop, "kernel_ms_per_step": kms,
+                     "step_tflops_survey_flop_model_per_gpu": survey_flop / (ms_dev * 1e-3) / 1e12,
+                     "kernel_share_of_step": kms["contract"] / ms_dev if ms_dev else None},
+        "clocks": clocks,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"], _ = cpu_baseline(plan)
+    if args.elide and rank == 0:
+        def step_elide():
+            table.run_dev(ncell, mz_d.data_ptr(), mz_d.data_ptr(), 1, w_d.data_ptr(), 0, scal_d.data_ptr(), phase_d.data_ptr(), elide=True)
+        for _ in range(2):
+            step_elide()
+        ms_el = timed(step_elide, args.steps) if world == 1 else None
+        line["elided"] = {"ms_per_step": ms_el, "grid_evals_per_sec": total_evals / world / (ms_el * 1e-3) if ms_el else None,
+                          "evaluated": table.last_stats()["evals"]}
+    if rank == 0:
+        print(json.dumps(line))
+    table.close()
+    if world > 1:
+        td.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

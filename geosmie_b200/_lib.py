@@ -43,6 +43,7 @@ SIGNATURES = {
     "gm_table_last_kernel_ms": (C.c_int, [vp, c_dp, c_dp, c_dp]),
     "gm_gsf_expand": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int]),
     "gm_gsf_expand_dev": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int]),
+    "gm_gsf_expand_phase4_dev": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int]),
     "gm_band_average": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int, vp]),
 }
 
@@ -156,6 +157,12 @@ class Handle:
         cnorm = np.empty(ncell)
         check(self.lib.gm_gsf_expand(self.h, ncell, ang.size, ptr(ang), ptr(F), ng, ptr(coef), ptr(cnorm), int(bool(quantize10))))
         return coef, cnorm
+
+    def gsf_expand_phase4_dev(self, ang_deg, ncell, p4_ptr, coef_ptr, cnorm_ptr, ng=129, quantize10=False):
+        """Device-pointer GSF expansion of gm_table_run's out_phase (asynchronous except for the small table upload)."""
+        ang = f64(ang_deg)
+        check(self.lib.gm_gsf_expand_phase4_dev(self.h, ncell, ang.size, ptr(ang), vp(p4_ptr), ng, vp(coef_ptr),
+                                                vp(cnorm_ptr) if cnorm_ptr else None, int(bool(quantize10))))
 
     def band_average(self, lam, v, lo, hi, use_wavenum):
         lam, v, lo, hi = f64(lam), f64(v), f64(lo), f64(hi)

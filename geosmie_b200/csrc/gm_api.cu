@@ -48,6 +48,8 @@ extern "C" int gm_destroy(gm_handle_t h) {
   if (!h) return GM_OK;
   cudaSetDevice(h->device);
   for (auto& b : h->ws) b.release();
+  h->gsf_nodes.release();
+  h->gsf_table.release();
   delete h;
   return GM_OK;
 }
@@ -272,8 +274,11 @@ struct gm_table_s {
   DevBuf coef, gact, scal_part, part, chunk_start, mz, mrel, wphase, wscal, out_scal, out_phase, stats, q, s12;
   double last_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int timing = 0;
-  cudaEvent_t ev[2] = {nullptr, nullptr};
+  std::vector<cudaEvent_t> evpool;   // pairs of events recorded around every launch of the last run (timing mode)
+  std::vector<int> evkind;           // 0 coeff, 1 contract, 2 finalize
+  size_t evused = 0;
   double ms_coeff = 0, ms_contract = 0, ms_finalize = 0;
+  int n_coeff = 0, n_contract = 0, n_finalize = 0;
 };
 
 extern "C" int gm_table_create(gm_handle_t h, int nx, const double* x, const int32_t* nmax, int nang, const double* cos_theta,
@@ -317,8 +322,7 @@ extern "C" int gm_table_destroy(gm_table_t t) {
   for (DevBuf* b : {&t->T, &t->cost, &t->coef, &t->gact, &t->scal_part, &t->part, &t->chunk_start, &t->mz, &t->mrel, &t->wphase,
                     &t->wscal, &t->out_scal, &t->out_phase, &t->stats, &t->q, &t->s12})
     b->release();
-  for (auto& e : t->ev)
-    if (e) cudaEventDestroy(e);
+  for (auto& e : t->evpool) cudaEventDestroy(e);
   delete t;
   return GM_OK;
 }
@@ -352,15 +356,39 @@ extern "C" int gm_table_set_bessel(gm_table_t t, const int64_t* off, const doubl
 extern "C" int gm_table_set_timing(gm_table_t t, int enable) {
   GM_REQUIRE(t != nullptr, "table is NULL");
   t->timing = enable;
-  if (enable && !t->ev[0]) {
-    GM_CUDA_TRY(cudaEventCreate(&t->ev[0]));
-    GM_CUDA_TRY(cudaEventCreate(&t->ev[1]));
-  }
   return GM_OK;
 }
 
+// record one event of a (begin, end) pair on the stream; events come from a grow-only pool, nothing synchronises here
+static int ev_mark(gm_table_t t, int kind) {
+  if (!t->timing) return GM_OK;
+  if (t->evused == t->evpool.size()) {
+    cudaEvent_t e;
+    GM_CUDA_TRY(cudaEventCreate(&e));
+    t->evpool.push_back(e);
+    t->evkind.push_back(kind);
+  }
+  t->evkind[t->evused] = kind;
+  GM_CUDA_TRY(cudaEventRecord(t->evpool[t->evused++], t->h->stream));
+  return GM_OK;
+}
+
+// sums the CUDA-event durations of the launches of the last run (synchronises the stream)
 extern "C" int gm_table_last_kernel_ms(gm_table_t t, double* a, double* b, double* c) {
   GM_REQUIRE(t != nullptr, "table is NULL");
+  if (t->timing && t->evused) {
+    GM_CUDA_TRY(cudaSetDevice(t->h->device));
+    GM_CUDA_TRY(cudaStreamSynchronize(t->h->stream));
+    t->ms_coeff = t->ms_contract = t->ms_finalize = 0;
+    t->n_coeff = t->n_contract = t->n_finalize = 0;
+    for (size_t i = 0; i + 1 < t->evused; i += 2) {
+      float ms = 0;
+      GM_CUDA_TRY(cudaEventElapsedTime(&ms, t->evpool[i], t->evpool[i + 1]));
+      if (t->evkind[i] == 0) { t->ms_coeff += ms; t->n_coeff++; }
+      if (t->evkind[i] == 1) { t->ms_contract += ms; t->n_contract++; }
+      if (t->evkind[i] == 2) { t->ms_finalize += ms; t->n_finalize++; }
+    }
+  }
   if (a) *a = t->ms_coeff;
   if (b) *b = t->ms_contract;
   if (c) *c = t->ms_finalize;
@@ -419,8 +447,7 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
   GM_CUDA_TRY(cudaMemsetAsync(t->stats.p, 0, sizeof(unsigned long long) * 8, st));
   const int smem = GM_STAGES * GM_STAGE_DBL * 8 + 2 * GM_STAGES * 8;
   const int64_t launches0 = h->launches;
-  t->ms_coeff = t->ms_contract = t->ms_finalize = 0;
-  float ms;
+  t->evused = 0;
 
   for (int t0 = 0; t0 < ntask; t0 += tb) {
     const int nt = std::min(tb, ntask - t0);
@@ -449,15 +476,10 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
     A.scal_part = t->scal_part.as<double>();
     A.q = d_q ? d_q + (size_t)t0 * G.nx * 6 : nullptr;
     A.stats = t->stats.as<unsigned long long>();
-    if (t->timing) GM_CUDA_TRY(cudaEventRecord(t->ev[0], st));
+    if ((rc = ev_mark(t, 0))) return rc;
     k_coeff<0><<<dim3((G.ngroup + 3) / 4, nt), 128, 0, st>>>(A);
     GM_LAUNCH_CHECK(h);
-    if (t->timing) {
-      GM_CUDA_TRY(cudaEventRecord(t->ev[1], st));
-      GM_CUDA_TRY(cudaEventSynchronize(t->ev[1]));
-      GM_CUDA_TRY(cudaEventElapsedTime(&ms, t->ev[0], t->ev[1]));
-      t->ms_coeff += ms;
-    }
+    if ((rc = ev_mark(t, 0))) return rc;
 
     ContractArgs C;
     memset(&C, 0, sizeof(C));
@@ -476,29 +498,19 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
     C.nx = G.nx;
     C.nang = t->nang;
     C.s12 = d_s12 ? d_s12 + (size_t)t0 * G.nx * t->nang * 4 : nullptr;
-    if (t->timing) GM_CUDA_TRY(cudaEventRecord(t->ev[0], st));
+    if ((rc = ev_mark(t, 1))) return rc;
     if (per_particle)
       k_contract<true><<<nt * 2 * nchunk, GM_CONTRACT_WARPS * 32, smem, st>>>(C);
     else
       k_contract<false><<<nt * 2 * nchunk, GM_CONTRACT_WARPS * 32, smem, st>>>(C);
     GM_LAUNCH_CHECK(h);
-    if (t->timing) {
-      GM_CUDA_TRY(cudaEventRecord(t->ev[1], st));
-      GM_CUDA_TRY(cudaEventSynchronize(t->ev[1]));
-      GM_CUDA_TRY(cudaEventElapsedTime(&ms, t->ev[0], t->ev[1]));
-      t->ms_contract += ms;
-    }
+    if ((rc = ev_mark(t, 1))) return rc;
     if (!per_particle) {
-      if (t->timing) GM_CUDA_TRY(cudaEventRecord(t->ev[0], st));
+      if ((rc = ev_mark(t, 2))) return rc;
       k_finalize<<<nt, GM_NANG_PAD, 0, st>>>(nchunk, G.ngroup, nmode, t->nang, t->part.as<double>(), t->scal_part.as<double>(),
                                              d_out_phase + (size_t)t0 * 4 * t->nang, d_out_scal + (size_t)t0 * nmode * GM_NSCAL);
       GM_LAUNCH_CHECK(h);
-      if (t->timing) {
-        GM_CUDA_TRY(cudaEventRecord(t->ev[1], st));
-        GM_CUDA_TRY(cudaEventSynchronize(t->ev[1]));
-        GM_CUDA_TRY(cudaEventElapsedTime(&ms, t->ev[0], t->ev[1]));
-        t->ms_finalize += ms;
-      }
+      if ((rc = ev_mark(t, 2))) return rc;
     }
   }
   t->last_stats[4] = (double)(h->launches - launches0);

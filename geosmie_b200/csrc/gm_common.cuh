@@ -65,6 +65,9 @@ struct gm_handle_s {
   // scratch for the per-particle API and GSF/bands
   DevBuf ws[16];
   size_t coef_budget_bytes = (size_t)2 << 30;  // coefficient staging buffer per gm_table_run batch
+  // GSF constants (Gauss nodes, interpolation brackets, generalized spherical functions) cached per angle grid
+  DevBuf gsf_nodes, gsf_table;
+  std::vector<double> gsf_key;
 };
 
 // ------------------------------------------------------------------------------------------------ table geometry

@@ -114,7 +114,8 @@ struct GsfNode {
   int i0, i1;        // indices of YY(I-1), YY(I) (0-based)
 };
 
-__global__ void __launch_bounds__(256) k_gsf(int nang, int ng, const double* __restrict__ F, const GsfNode* __restrict__ nodes,
+// nrow = 6: F rows are F11,F22,F33,F44,F12,F34.  nrow = 4: rows are P11,P12,P33,P34 of gm_table_run (P22 = P11, P44 = P33).
+__global__ void __launch_bounds__(256) k_gsf(int nrow, int nang, int ng, const double* __restrict__ F, const GsfNode* __restrict__ nodes,
                                              const double* __restrict__ G, double* __restrict__ coef, double* __restrict__ cnorm,
                                              int quantize10) {
   extern __shared__ double sm[];
@@ -122,8 +123,12 @@ __global__ void __launch_bounds__(256) k_gsf(int nang, int ng, const double* __r
   double* ff = sm + 6 * nang;     // [6][ng]: FF11, FP, FM, FF44, FF12, FF34
   double* res = ff + 6 * ng;      // [6][ng]
   const int cell = blockIdx.x;
-  const double* Fc = F + (size_t)cell * 6 * nang;
-  for (int k = threadIdx.x; k < 6 * nang; k += blockDim.x) f[k] = Fc[k];
+  const double* Fc = F + (size_t)cell * nrow * nang;
+  for (int k = threadIdx.x; k < 6 * nang; k += blockDim.x) {
+    int row = k / nang;
+    if (nrow == 4) row = (row == 0 || row == 1) ? 0 : (row == 2 || row == 3) ? 2 : (row == 4 ? 1 : 3);
+    f[k] = Fc[row * nang + k % nang];
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < ng; i += blockDim.x) {
     const GsfNode nd = nodes[i];
@@ -174,10 +179,7 @@ __global__ void __launch_bounds__(256) k_gsf(int nang, int ng, const double* __r
   if (threadIdx.x == 0 && cnorm) cnorm[cell] = cn;
 }
 
-int gsf_core(gm_handle_t h, int ncell, int nang, const double* h_ang_deg, const double* d_F, int ng, double* d_coef,
-             double* d_cnorm, int quantize10) {
-  GM_REQUIRE(ng >= 3 && ng <= 2048, "ng out of range");
-  GM_REQUIRE(nang >= 2 && nang <= 1000, "nang out of range (NANG_MAX = 1000, params.h:1)");
+int gsf_upload_constants(gm_handle_t h, int nang, const double* h_ang_deg, int ng) {
   cudaStream_t st = h->stream;
   std::vector<double> X, W, G;
   gauss_nodes(ng, X, W);
@@ -212,14 +214,30 @@ int gsf_core(gm_handle_t h, int ncell, int nang, const double* h_ang_deg, const 
     nodes[i].w = W[i];
   }
   int rc;
-  if ((rc = h->ws[0].ensure(sizeof(GsfNode) * ng)) || (rc = h->ws[1].ensure(sizeof(double) * G.size()))) return rc;
-  GM_CUDA_TRY(cudaMemcpyAsync(h->ws[0].p, nodes.data(), sizeof(GsfNode) * ng, cudaMemcpyHostToDevice, st));
-  GM_CUDA_TRY(cudaMemcpyAsync(h->ws[1].p, G.data(), sizeof(double) * G.size(), cudaMemcpyHostToDevice, st));
+  if ((rc = h->gsf_nodes.ensure(sizeof(GsfNode) * ng)) || (rc = h->gsf_table.ensure(sizeof(double) * G.size()))) return rc;
+  GM_CUDA_TRY(cudaMemcpyAsync(h->gsf_nodes.p, nodes.data(), sizeof(GsfNode) * ng, cudaMemcpyHostToDevice, st));
+  GM_CUDA_TRY(cudaMemcpyAsync(h->gsf_table.p, G.data(), sizeof(double) * G.size(), cudaMemcpyHostToDevice, st));
+  GM_CUDA_TRY(cudaStreamSynchronize(st));  // nodes/G are stack-owned
+  return GM_OK;
+}
+
+int gsf_core(gm_handle_t h, int ncell, int nang, const double* h_ang_deg, const double* d_F, int ng, double* d_coef,
+             double* d_cnorm, int quantize10, int nrow = 6) {
+  GM_REQUIRE(ng >= 3 && ng <= 2048, "ng out of range");
+  GM_REQUIRE(nang >= 2 && nang <= 1000, "nang out of range (NANG_MAX = 1000, params.h:1)");
+  cudaStream_t st = h->stream;
+  // the constants depend only on (ng, angle grid): build and upload them once per grid
+  std::vector<double> key(h_ang_deg, h_ang_deg + nang);
+  key.push_back((double)ng);
+  if (key != h->gsf_key) {
+    int rc0 = gsf_upload_constants(h, nang, h_ang_deg, ng);
+    if (rc0) return rc0;
+    h->gsf_key = key;
+  }
   const size_t smem = sizeof(double) * (6 * (size_t)nang + 12 * (size_t)ng);
   GM_CUDA_TRY(cudaFuncSetAttribute(k_gsf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_gsf<<<ncell, 256, smem, st>>>(nang, ng, d_F, h->ws[0].as<GsfNode>(), h->ws[1].as<double>(), d_coef, d_cnorm, quantize10);
+  k_gsf<<<ncell, 256, smem, st>>>(nrow, nang, ng, d_F, h->gsf_nodes.as<GsfNode>(), h->gsf_table.as<double>(), d_coef, d_cnorm, quantize10);
   GM_LAUNCH_CHECK(h);
-  GM_CUDA_TRY(cudaStreamSynchronize(st));  // nodes/G are stack-owned
   return GM_OK;
 }
 
@@ -231,6 +249,14 @@ extern "C" int gm_gsf_expand_dev(gm_handle_t h, int ncell, int nang, const doubl
   GM_REQUIRE(ncell > 0, "ncell must be > 0");
   GM_CUDA_TRY(cudaSetDevice(h->device));
   return gsf_core(h, ncell, nang, ang_deg, F, ng, coef, cnorm, quantize10);
+}
+
+extern "C" int gm_gsf_expand_phase4_dev(gm_handle_t h, int ncell, int nang, const double* ang_deg, const double* P4, int ng,
+                                        double* coef, double* cnorm, int quantize10) {
+  GM_REQUIRE(h && ang_deg && P4 && coef, "NULL argument");
+  GM_REQUIRE(ncell > 0, "ncell must be > 0");
+  GM_CUDA_TRY(cudaSetDevice(h->device));
+  return gsf_core(h, ncell, nang, ang_deg, P4, ng, coef, cnorm, quantize10, 4);
 }
 
 extern "C" int gm_gsf_expand(gm_handle_t h, int ncell, int nang, const double* ang_deg, const double* F, int ng, double* coef,

@@ -1,0 +1,594 @@
+"""GPU table driver: mirror of src/geosmie/dointegration.py (Mie branch) on top of libgeosmie_b200.
+
+The reference walks bin -> wavelength -> RH and, per cell, calls rawMie (per-particle Mie at every x, S1/S2 at 371
+angles, Mueller elements) and integratePSD (size-distribution reduction).  Here the per-cell inputs (refractive index,
+number weights) are still produced on the host with the reference's own formulas, but ALL cells of a bin go to the GPU
+in one call (gm_table_run): the per-particle S1/S2 are never materialised, only the reduced sums come back, and
+`combine_modes` / `postprocess` then apply integratePSD's closing arithmetic and the a-posteriori steps of `fun`
+vectorised over cells.  Kernel-mode (GRASP/Saito) dust is out of scope (no Mie; external kernel files).
+"""
+import os
+import sys
+
+import numpy as np
+from scipy.interpolate import interp1d
+
+from . import _lib, ncio
+from . import particleparams as pp
+from .pymiecoated.mie_coated import MultipleMie
+from .pymiecoated.mie_coeffs import nmax_of
+
+# key groups, same names and order as the reference (dointegration.py:16-24); the order of scalarkeys matters (:1156-1157)
+scatkeys = ['p11', 'p12', 'p22', 'p33', 'p34', 'p44']
+scalarkeys = ['qext', 'qsca', 'qabs', 'qb', 'g', 'csca', 'cext']
+extrakeys = ['ssa', 'bsca', 'bext', 'bbck', 'refreal', 'refimag', 'lidar_ratio']
+elekeys = ['pback']
+nlscalarkeys = ['mass', 'volume', 'area', 'rEff', 'rMass', 'rhop', 'growth_factor', 'rLow', 'rUp']
+allkeys = scatkeys + scalarkeys + extrakeys + elekeys + nlscalarkeys
+
+_S = _lib  # raw-sum indices S_W ... S_CEXT
+_trapz = getattr(np, "trapezoid", None) or np.trapz
+
+
+# ----------------------------------------------------------------------------------------------- grids
+def table_angles():
+    """The 371 output scattering angles in degrees (dointegration.py:739-742)."""
+    return np.concatenate([np.linspace(0., 1., 100, endpoint=False), np.linspace(1., 10., 100, endpoint=False),
+                           np.linspace(10., 180., 171, endpoint=True)])
+
+
+def getDR(arr):
+    """Centred bin widths of a grid (dointegration.py:93-101)."""
+    arr = np.asarray(arr, dtype=float)
+    out = np.empty_like(arr)
+    out[0] = arr[1] - arr[0]
+    out[-1] = arr[-1] - arr[-2]
+    out[1:-1] = ((arr[1:-1] - arr[:-2]) + (arr[2:] - arr[1:-1])) / 2.
+    return out
+
+
+def getXArrCarma(minx, maxx, nbinperdecade):
+    """CARMA-style grid, geometric in volume (dointegration.py:103-153).  The loop form keeps the reference's
+    floating-point sequence (rvolmin * rmRat ** i evaluated per point)."""
+    rat = maxx / minx
+    nbin = np.log10(maxx / minx) * nbinperdecade
+    rmRat = (rat ** 3) ** (1. / nbin)
+    rMin = minx * ((1. + rmRat) / 2.) ** (1. / 3.)
+    cpi = 4. / 3. * np.pi
+    rvolmin = cpi * rMin ** 3.
+    vrfact = ((3. / 2. / np.pi / (rmRat + 1)) ** (1. / 3.)) * (rmRat ** (1. / 3.) - 1.)
+    r, dr = [], []
+    for i in range(int(nbin)):
+        rvol = rvolmin * rmRat ** i
+        r.append((rvol / cpi) ** (1. / 3.))
+        dr.append(vrfact * (rvol) ** (1. / 3.))
+    return np.array(r), np.array(dr)
+
+
+def initializeXarr(params, radind, minlam, maxlam):
+    """Per-bin size-parameter grid shared by all wavelengths and RH (dointegration.py:425-463)."""
+    pparam = params['psd']['params']
+    psdtype = params['psd']['type']
+    if psdtype == 'lognorm':
+        lo = pparam['rmin0'][radind][0] * 2 * np.pi / maxlam
+        hi = pparam['rmax0'][radind][-1] * 2 * np.pi / minlam * 3.0
+        if 'numperdec' not in pparam:
+            print("numperdec missing from dict")
+            sys.exit()
+        return getXArrCarma(lo, hi, pparam['numperdec'][radind])
+    if psdtype == 'ss':
+        lo = pparam['rMinMaj'][radind] * 2 * np.pi / maxlam
+        hi = pparam['rMaxMaj'][radind] * 2 * np.pi / minlam * 10
+        return getXArrCarma(lo, hi, pparam['numperdec'][radind])
+    if psdtype == 'du':
+        lo = pparam['rMinMaj'][radind][0] * 2 * np.pi / maxlam
+        hi = pparam['rMaxMaj'][radind][-1] * 2 * np.pi / minlam
+        return (np.linspace(np.log10(lo), np.log10(hi), 1000)) ** 10., None
+    raise ValueError("unknown psd type %r" % psdtype)
+
+
+# ----------------------------------------------------------------------------------------------- per-cell host inputs
+def getHumidRefractiveIndex(params, radind, rhi, rh, nref0, nrefwater):
+    """Volume mixing with water, n = n_w + (n_0 - n_w) rrat^3 (dointegration.py:493-536).  Returns mr, mi, gf, rrat."""
+    pparam = params['psd']['params']
+    rparams = params['rhDep']
+    typ = rparams['type']
+    if typ == 'simple' or (typ == 'trivial' and rhi == 0):
+        gf = rparams['params']['gf'][rhi]
+        rrat = (1. / gf)
+    elif typ in ('ss', 'su'):
+        if typ == 'ss':
+            try:
+                rMinMaj = pparam['rMinMaj'][radind]
+            except Exception:
+                rMinMaj = pparam['rmin0'][radind][0]
+        else:
+            rMinMaj = pparam['rmin0'][radind][0]
+        rMinUse = pp.humidityGrowth(rparams, rMinMaj, rh[rhi], rh)
+        rrat = (rMinMaj / rMinUse)
+        gf = 1. / rrat
+    else:
+        print("PROBLEM! NO RHDEP DEFINED!")
+        sys.exit()
+    nrefUse = [nrefwater + (n0 - nrefwater) * (rrat) ** 3. for n0 in nref0]
+    return [n.real for n in nrefUse], [n.imag for n in nrefUse], gf, rrat
+
+
+def calculatePSD(params, radind, onerh, rh, xxarr, drarr, rrat, lam):
+    """Number weights per grid point for every mode of the bin (dointegration.py:539-664).
+    Returns psd (list of arrays summing to 1), ref (mass-effective radii), rLow, rUp."""
+    pparam = params['psd']['params']
+    psdtype = params['psd']['type']
+    rparams = params['rhDep']
+    rarr = xxarr / (2 * np.pi / lam)
+    rr = xxarr * lam / 2. / np.pi
+    psd, ref = [], []
+    if psdtype == 'lognorm':
+        rmodes = [pp.humidityGrowth(rparams, r0, onerh, rh) for r0 in pparam['r0'][radind]]
+        rmaxs0 = list(pparam['rmax0'][radind])
+        rmaxs = [pp.humidityGrowth(rparams, r, onerh, rh) for r in rmaxs0]
+        rmins = list(pparam['rmin0'][radind])      # rmin does not grow with humidity
+        rLow, rUp = rmins[0], rmaxs0[0]
+        sigmas = pparam['sigma'][radind]
+        for k in range(len(rmodes)):
+            w = pp.getLogNormPSD(rmodes[k], sigmas[k], xxarr, lam, rmaxs[k], rmins[k])   # dN/dr
+            w *= drarr                                                                   # -> dN
+            w /= np.sum(w)
+            psd.append(w)
+            ref.append(np.sum(rr ** 4. * w) / np.sum(rr ** 3. * w))
+    elif psdtype == 'ss':
+        rMinMaj, rMaxMaj = pparam['rMinMaj'][radind], pparam['rMaxMaj'][radind]
+        rLow, rUp = rMinMaj, rMaxMaj
+        rMinUse = pp.humidityGrowth(rparams, rMinMaj, onerh, rh)
+        rMaxUse = pp.humidityGrowth(rparams, rMaxMaj, onerh, rh)
+        rrat = (rMinMaj / rMinUse)
+        dr = getDR(rarr)
+        r80rat = 1.65 * rrat
+        r80 = rarr * r80rat * 1e6
+        aFac = 4.7 * (1. + 30. * r80) ** (-0.017 * r80 ** (-1.44))
+        bFac = (0.433 - np.log10(r80)) / 0.433
+        dndr = 1.373 * r80 ** (-aFac) * (1. + 0.057 * r80 ** 3.45) * 10. ** (1.607 * np.exp(-bFac ** 2.)) * r80rat
+        dndr[rarr < rMinUse] = 0.
+        dndr[rarr > rMaxUse] = 0.
+        dndr = dndr / np.sum(dndr)
+        w = dndr * dr
+        w /= np.sum(w)
+        psd = [w]
+        ref = [np.sum(rr ** 4 * w) / np.sum(rr ** 3 * w)]
+    elif psdtype == 'du':
+        for rMinMaj, rMaxMaj in zip(pparam['rMinMaj'][radind], pparam['rMaxMaj'][radind]):
+            rLow, rUp = rMinMaj, rMaxMaj
+            dndr = rarr ** (-4.)
+            dndr[rarr < rMinMaj] = 0.
+            dndr[rarr > rMaxMaj] = 0.
+            if np.max(dndr) == 0.:
+                print('prc:', np.min(xxarr), np.max(xxarr), np.min(rarr), np.max(rarr), lam, rMinMaj, rMaxMaj)
+                sys.exit()
+            w = dndr * getDR(xxarr)
+            w /= np.sum(w)
+            psd.append(w)
+            ref.append(np.sum(rr ** 4. * w) / np.sum(rr ** 3. * w))
+    else:
+        raise ValueError("unknown psd type %r" % psdtype)
+    return psd, ref, rLow, rUp
+
+
+# ----------------------------------------------------------------------------------------------- reductions
+def combine_modes(scal, phase, fracs, lam, reff0, rhop0, rhop):
+    """integratePSD's closing arithmetic (dointegration.py:1104-1200) from the GPU raw sums.
+
+    scal  [..., nmode, GM_NSCAL] raw sums in size-parameter space (r = x lam / 2 pi is applied here)
+    phase [..., 4, nang]         sum_x w P(x, theta), already weighted by the mode fractions
+    fracs, reff0 [nmode]; lam, rhop0, rhop broadcastable to the leading dims.  Returns the `ret` dict of integratePSD.
+    """
+    scal = np.asarray(scal, dtype=float)
+    lead = scal.shape[:-2]
+    nmode = scal.shape[-2]
+    c = np.asarray(lam, dtype=float) / (2. * np.pi)
+    c = np.broadcast_to(c, lead)[..., None]
+    rhop = np.broadcast_to(np.asarray(rhop, dtype=float), lead)[..., None]
+    rhop0 = np.broadcast_to(np.asarray(rhop0, dtype=float), lead)[..., None]
+    fr = np.asarray(fracs, dtype=float).reshape((1,) * len(lead) + (nmode,))
+    reff0 = np.asarray(reff0, dtype=float)
+    if reff0.ndim == 1:
+        reff0 = reff0.reshape((1,) * len(lead) + (nmode,))
+    S = lambda k: scal[..., k]
+    num = S(_S.S_W)
+    r2, r3, r4 = c ** 2 * S(_S.S_X2W), c ** 3 * S(_S.S_X3W), c ** 4 * S(_S.S_X4W)
+    t = {}
+    t['num'] = num
+    t['area'] = np.pi * r2 / num
+    t['volume'] = 4. / 3. * np.pi * r3 / num
+    t['mass'] = t['volume'] * rhop
+    t['rEff'] = r3 / r2
+    reff_mass = r4 / r3
+    t['rMass'] = 4. / 3. * np.pi * rhop * reff_mass ** 3.
+    rMass0 = 4. / 3. * np.pi * rhop0 * reff0 ** 3
+    # area-weighted efficiencies ('dumix', :1188-1190); the (lam/2pi)^2 factors cancel in the ratios
+    t['qext'] = S(_S.S_QEXT) / S(_S.S_X2W)
+    t['qsca'] = S(_S.S_QSCA) / S(_S.S_X2W)
+    t['qabs'] = S(_S.S_QABS) / S(_S.S_X2W)
+    # qb through the backed-out P11(180) (:1133-1145, :1168-1169)
+    p11back = 4. * np.pi * S(_S.S_QB) / S(_S.S_QSCA)
+    t['qb'] = p11back * t['qsca'] / (4. * np.pi)
+    # keys after 'g' carry the (area * qsca) weight because of the in-place `thisweight *= qsca` (:1111-1112, :1157)
+    t['g'] = S(_S.S_G) / S(_S.S_QSCA)
+    t['csca'] = np.pi * c ** 2 * S(_S.S_CSCA) / S(_S.S_QSCA)
+    t['cext'] = np.pi * c ** 2 * S(_S.S_CEXT) / S(_S.S_QSCA)
+    conv = 1. / rhop / t['rEff'] * t['rMass'] / rMass0            # :1193
+    t['bsca'] = 3. / 4. * t['qsca'] * conv
+    t['bext'] = 3. / 4. * t['qext'] * conv
+    t['bbck'] = 3. / 4. * t['qb'] * conv / (4 * np.pi)
+    ret = {k: np.sum(fr * v, axis=-1) for k, v in t.items()}       # ret[key] += frac * thisret[key], :1199-1200
+    ret['lidar_ratio'] = np.zeros(lead)
+    ph = np.asarray(phase, dtype=float)
+    ret['p11'] = ph[..., 0, :]
+    ret['p12'] = ph[..., 1, :]
+    ret['p22'] = ph[..., 0, :].copy()
+    ret['p33'] = ph[..., 2, :]
+    ret['p34'] = ph[..., 3, :]
+    ret['p44'] = ph[..., 2, :].copy()
+    return ret
+
+
+def postprocess(ret, ang):
+    """Extra variables and the a-posteriori phase-matrix normalisation of `fun` (dointegration.py:950-988)."""
+    ret['lidar_ratio'] = ret['qext'] / ret['qb'] * 4 * np.pi
+    ret['ssa'] = ret['qsca'] / ret['qext']
+    theta = np.radians(ang)
+    p11 = ret['p11']
+    p11n = 2. * p11 / _trapz(p11 * np.sin(theta), theta)[..., None]
+    for k in ('p12', 'p22', 'p33', 'p34', 'p44'):
+        ret[k] = ret[k] * p11n / p11
+    ret['p11'] = p11n
+    ret['pback'] = np.stack([ret[k][..., -1] for k in ('p11', 'p12', 'p33', 'p34', 'p22', 'p44')], axis=-1)
+    return ret
+
+
+# ----------------------------------------------------------------------------------------------- reference-shaped API
+class RawMie(dict):
+    """Return value of rawMie: the reference's dict of per-particle arrays, plus what integratePSD needs to run the
+    fused GPU reduction instead of re-reducing the arrays on the host."""
+    mm = None
+    m = None
+
+
+def rawMie(mm, scatkeys_, scalarkeys_, lam, mr, mi, psd, costarr):
+    """Per-particle Mie over the grid of `mm` at one refractive index (dointegration.py:1211-1254): efficiencies,
+    csca/cext and the six Mueller elements [nx, nang], computed on the GPU (DMMA per-particle path)."""
+    x = np.asarray(mm.xArr, dtype=float)
+    rr = x * lam / (2. * np.pi)
+    q, s12 = mm.calculateS12SizeRangeArrays(mr, mi)
+    s1 = s12[..., 0] + 1j * s12[..., 1]
+    s2 = s12[..., 2] + 1j * s12[..., 3]
+    ret = RawMie()
+    ret.mm, ret.m = mm, (mr, mi)
+    a1, a2 = np.abs(s1) ** 2, np.abs(s2) ** 2
+    vals = {'p11': 0.5 * (a1 + a2), 'p12': 0.5 * (a2 - a1), 'p22': 0.5 * (a1 + a2), 'p33': (s1 * np.conj(s2)).real,
+            'p34': -(np.conj(s1) * s2).imag, 'p44': (s1 * np.conj(s2)).real,
+            'qext': q[:, 0], 'qsca': q[:, 1], 'qabs': q[:, 2], 'qb': q[:, 3], 'g': q[:, 4],
+            'csca': q[:, 1] * np.pi * rr ** 2, 'cext': q[:, 0] * np.pi * rr ** 2}
+    for k in list(scatkeys_) + list(scalarkeys_):
+        ret[k] = vals[k]
+    return ret
+
+
+def integratePSD(xxarr, rawret, psd, fracs, lam, reff0, rhop0, rhop):
+    """Size-distribution integration of rawMie results (dointegration.py:1064-1209).  `rawret` must come from this
+    module's rawMie: the reduction is re-run fused on the GPU (gm_table_run) from the (table, m) each entry carries."""
+    tables = [r.mm.device_table() for r in rawret]
+    nmode = len(fracs)
+    ws = np.asarray(psd, dtype=float)
+    same = all(r.m == rawret[0].m for r in rawret)
+    if same:
+        m = complex(*rawret[0].m)
+        mz = [np.sqrt(m ** 2 * 1.0)]
+        wp = np.tensordot(np.asarray(fracs, dtype=float), ws, axes=(0, 0))[None]
+        scal, phase = tables[0].run(mz, mz, wp, ws[None])
+        return combine_modes(scal[0], phase[0], fracs, lam, reff0, rhop0, rhop)
+    mz = [np.sqrt(complex(*r.m) ** 2 * 1.0) for r in rawret]
+    wp = np.asarray(fracs, dtype=float)[:, None] * ws
+    scal, phase = tables[0].run(mz, mz, wp, ws[:, None, :])
+    return combine_modes(scal[:, 0, :], phase.sum(axis=0), fracs, lam, reff0, rhop0, rhop)
+
+
+# ----------------------------------------------------------------------------------------------- file layout
+_VARMETA = {
+    'p11': ('dimensionless', 'P11 element of the normalized scattering matrix'),
+    'p12': ('dimensionless', 'P12 element of the normalized scattering matrix'),
+    'p22': ('dimensionless', 'P22 element of the normalized scattering matrix'),
+    'p33': ('dimensionless', 'P33 element of the normalized scattering matrix'),
+    'p34': ('dimensionless', 'P34 element of the normalized scattering matrix'),
+    'p44': ('dimensionless', 'P44 element of the normalized scattering matrix'),
+    'qsca': ('dimensionless', 'scattering efficiency'),
+    'qabs': ('dimensionless', 'absorption efficiency'),
+    'qext': ('dimensionless', 'extinction efficiency'),
+    'g': ('dimensionless', 'asymmetry factor'),
+    'ssa': ('dimensionless', 'single-scattering albedo'),
+    'qb': ('dimensionless', 'backscattering efficiency'),
+    'bsca': ('m2 (kg dry mass)-1', 'mass scattering efficiency'),
+    'bext': ('m2 (kg dry mass)-1', 'mass extinction efficiency'),
+    'csca': ('m2', 'mass scattering cross-section'),
+    'cext': ('m2', 'mass extinction cross-section'),
+    'bbck': ('m2 (kg dry mass)-1 sr-1', 'mass backscatter efficiency'),
+    'lidar_ratio': ('', 'lidar ratio'),
+    'mass': ('kg', 'particle mass'),
+    'volume': ('m3 kg-1', 'particle volume per kg dry mass'),
+    'area': ('m2 kg-1', 'particle cross sectional area per kg dry mass'),
+    'rEff': ('m', 'effective radius of bin'),
+    'rMass': ('kg', 'effective mass of wet particle'),
+    'rUp': ('m', 'upper edge of radius bin'),
+    'rLow': ('m', 'lower edge of radius bin'),
+    'pback': ('dimensionless', 'phase function in backscatter direction, ordered as P11, P12, P33, P34, P22, P44'),
+    'rhop': ('kg m-3', 'wet particle density'),
+    'growth_factor': ('fraction', 'growth factor = ratio of wet to dry particle radius'),
+    'refreal': ('dimensionless', 'real refractive index of wet particle'),
+    'refimag': ('dimensionless', 'imaginary refractive index of wet particle'),
+}
+# creation order of the data variables in the reference file (dointegration.py:366-397)
+_VARORDER = ['p11', 'p12', 'p22', 'p33', 'p34', 'p44', 'qsca', 'qabs', 'qext', 'g', 'ssa', 'qb', 'bsca', 'bext', 'csca',
+             'cext', 'bbck', 'lidar_ratio', 'mass', 'volume', 'area', 'rEff', 'rMass', 'rUp', 'rLow', 'pback', 'rhop',
+             'growth_factor', 'refreal', 'refimag']
+
+
+def _dimtypes(oppclassic):
+    radius, lamb, npol = ('radius', 'lambda', 'nPol') if oppclassic else ('bin', 'wavelength', 'p')
+    if oppclassic:
+        kinds = {"scal": (radius, "rh", lamb), "nl": (radius, "rh"), "scat": (radius, "rh", lamb, "ang"),
+                 "ele": (npol, radius, "rh", lamb)}
+    else:
+        kinds = {"scal": (radius, lamb, "rh"), "nl": (radius, "rh"), "scat": (radius, lamb, "rh", "ang"),
+                 "ele": (radius, lamb, "rh", "p")}
+    return radius, lamb, npol, kinds
+
+
+def _kind_of(key):
+    if key in scatkeys:
+        return "scat"
+    if key in elekeys:
+        return "ele"
+    if key in nlscalarkeys:
+        return "nl"
+    return "scal"
+
+
+def createNCDF(ncdfID, oppfx, rarr, rharr, lambarr, ang, oppclassic):
+    """Create the output file with the reference's dimensions, variables, attributes and order
+    (dointegration.py:205-422): optics_<id>.nomom[.legacy].nc4."""
+    radius, lamb, npol, kinds = _dimtypes(oppclassic)
+    fn = 'optics_%s.nomom.legacy.nc4' % ncdfID if oppclassic else 'optics_%s.nomom.nc4' % ncdfID
+    nc = ncio.Dataset(os.path.join(oppfx, fn), 'w')
+    nc.createDimension('rh', len(rharr))
+    nc.createDimension(lamb, len(lambarr))
+    nc.createDimension(radius, len(rarr))
+    nc.createDimension(npol, 6)
+    nc.createDimension('ang', len(ang))
+    coord = [('rh', 'f8', 'fraction', 'relative humidity', rharr),
+             (lamb, 'f8', 'm', 'wavelength', lambarr),
+             (radius, 'i8', 'dimensionless', 'radius bin index (1-indexed)', range(1, len(rarr) + 1)),
+             (npol, 'i8', 'dimensionless', 'Scattering matrix element index, ordered as P11, P12, P33, P34, P22, P44',
+              [11, 12, 33, 34, 22, 44]),
+             ('ang', 'f8', 'degrees', 'scattering angle', ang)]
+    for name, dt, units, long_name, values in coord:
+        v = nc.createVariable(name, dt, (name), compression='zlib')
+        v.long_name = long_name
+        v.units = units
+        v[:] = np.asarray(list(values))
+    for key in _VARORDER:
+        v = nc.createVariable(key, 'f8', kinds[_kind_of(key)], compression='zlib')
+        v.long_name = _VARMETA[key][1]
+        v.units = _VARMETA[key][0]
+    return nc
+
+
+# ----------------------------------------------------------------------------------------------- the table build
+def bins_of(params):
+    """Bin indices and nominal radii (dointegration.py:713-725)."""
+    p = params['psd']['params']
+    t = params['psd']['type']
+    if t == 'lognorm':
+        return list(range(len(p['r0']))), list(p['r0'])
+    if t == 'ss':
+        return list(range(len(p['rMinMaj']))), list(p['rMinMaj'])
+    if t == 'du':
+        return list(range(len(p['rMinMaj']))), [xx[0] for xx in p['rMinMaj']]
+    raise ValueError("unknown psd type %r" % t)
+
+
+class BinPlan(object):
+    """Host-side description of one size bin: the grid and, for every (wavelength, RH) cell that must be computed, the
+    refractive indices, number weights and scalars that the reference derives inside its lambda/RH loops
+    (dointegration.py:811-889).  `tasks` flattens the cells into gm_table_run tasks."""
+
+    def __init__(self, params, radind, lambarr, rh_used, part_m, water_m, cells=None):
+        self.radind = radind
+        self.xx, self.dr = initializeXarr(params, radind, lambarr[0], lambarr[-1])
+        self.nmax = nmax_of(self.xx)
+        pparam = params['psd']['params']
+        trivial = params['rhDep']['type'] == 'trivial'
+        rhop00 = params['rhop0']
+        self.rhop0 = rhop00[radind] if isinstance(rhop00, list) else rhop00
+        self.fracs = list(pparam['fracs'][radind])
+        nlam, nrh = len(lambarr), len(rh_used)
+        self.nri = len(part_m)
+        self.cells = []          # (li, rhi)
+        self.trivial = trivial
+        mr_l, w_l, meta = [], [], []
+        want = None if cells is None else set(cells)
+        for li, lam in enumerate(lambarr):
+            nref0 = [complex(f[0](lam), -f[1](lam)) for f in part_m]      # sign flip of the stored -k (:813-816)
+            nrefwater = complex(1, 0) if trivial else complex(water_m[0](lam), water_m[1](lam))
+            _, _, _, rrat0 = getHumidRefractiveIndex(params, radind, 0, rh_used, nref0, nrefwater)
+            _, reff_mass0, _, _ = calculatePSD(params, radind, 0., rh_used, self.xx, self.dr, rrat0, lam)
+            for rhi, onerh in enumerate(rh_used):
+                if trivial and rhi > 0:
+                    continue
+                if want is not None and (li, rhi) not in want:
+                    continue
+                mr, mi, gf, rrat = getHumidRefractiveIndex(params, radind, rhi, rh_used, nref0, nrefwater)
+                psd, ref, rLow, rUp = calculatePSD(params, radind, onerh, rh_used, self.xx, self.dr, rrat, lam)
+                rhop = rrat ** 3. * self.rhop0 + (1. - rrat ** 3.) * 1000.
+                self.cells.append((li, rhi))
+                mr_l.append([complex(a, b) for a, b in zip(mr, mi)])
+                w_l.append(np.asarray(psd))
+                meta.append((lam, rhop, gf, rLow, rUp, list(reff_mass0)))
+        self.m = np.array(mr_l, dtype=np.complex128).reshape(len(self.cells), self.nri)
+        self.w = np.array(w_l, dtype=float).reshape(len(self.cells), len(self.fracs), self.xx.size)
+        self.lam = np.array([a[0] for a in meta])
+        self.rhop = np.array([a[1] for a in meta])
+        self.gf = np.array([a[2] for a in meta])
+        self.rLow = np.array([a[3] for a in meta])
+        self.rUp = np.array([a[4] for a in meta])
+        self.reff0 = np.array([a[5] for a in meta]).reshape(len(self.cells), len(self.fracs))
+
+    # ---- flatten to GPU tasks
+    def tasks(self):
+        """Returns (mz [ntask], w_phase [ntask][nx], w_scal [ntask][nmode_t][nx], tasks_per_cell)."""
+        fr = np.asarray(self.fracs, dtype=float)
+        ncell, nmode, nx = self.w.shape
+        if self.nri == 1:
+            # one Mie evaluation per cell, shared by all modes (allret replicated, dointegration.py:882-884)
+            mz = np.sqrt(self.m[:, 0] ** 2 * 1.0)
+            wp = np.tensordot(self.w, fr, axes=(1, 0))
+            return mz, wp, self.w, 1
+        assert self.nri == nmode, "one refractive index per PSD mode expected"
+        mz = np.sqrt(self.m.reshape(-1) ** 2 * 1.0)
+        wp = (self.w * fr[None, :, None]).reshape(ncell * nmode, nx)
+        return mz, wp, self.w.reshape(ncell * nmode, 1, nx), nmode
+
+    def reduce(self, scal, phase, tasks_per_cell):
+        """Raw sums of the tasks -> the integratePSD `ret` dict with a leading cell axis."""
+        ncell = len(self.cells)
+        if tasks_per_cell == 1:
+            sc, ph = scal, phase
+        else:
+            sc = scal.reshape(ncell, tasks_per_cell, scal.shape[-1])
+            ph = phase.reshape(ncell, tasks_per_cell, 4, phase.shape[-1]).sum(axis=1)
+        return combine_modes(sc, ph, self.fracs, self.lam, self.reff0, self.rhop0, self.rhop)
+
+
+def run_bin(plan, costarr, handle=None, elide=True, table=None):
+    """GPU evaluation of every cell of a bin.  Returns (ret dict with leading cell axis, table)."""
+    own = table is None
+    if own:
+        table = _lib.Table(plan.xx, plan.nmax, costarr, handle)
+    mz, wp, ws, tpc = plan.tasks()
+    scal, phase = table.run(mz, mz, wp, ws, elide=elide)
+    ret = plan.reduce(scal, phase, tpc)
+    return ret, table
+
+
+def fun(partID0, datatype, oppfx, oppclassic, elide=True, write=True, comm=None):
+    """Main table build called from runoptics.py (dointegration.py:672-1036).  Same arguments as the reference plus
+    `elide` (skip exactly-zero-weight particles; result-neutral), `write` (False: return the arrays only) and `comm`
+    (a geosmie_b200.dist.Comm: cells are sharded across ranks and gathered to rank 0).  Returns the dict of arrays
+    written to optics_<id>.nomom[.legacy].nc4 on rank 0 (None elsewhere)."""
+    partID = partID0.split('/')[-1].replace(".json", "")
+    print("\n ####################\n Starting case %s\n ####################\n" % partID)
+    partID2 = partID0.replace('-orig', '') if '-orig' in partID else partID0
+    params = pp.getParticleParams(partID2, datatype)
+    mode = params.get('mode', 'mie')
+    if mode != 'mie':
+        raise NotImplementedError("mode %r (GRASP/Saito kernels) is outside the Mie hot path of this build" % mode)
+    mList = params['mList']
+    lambarr = mList[0][0]
+    part_m = [(interp1d(m[0], m[1]), interp1d(m[0], m[2])) for m in mList]
+    water_m = None
+    if params['rhDep']['type'] != 'trivial':
+        wl = pp.getWaterM()
+        water_m = (interp1d(wl[0], wl[1]), interp1d(wl[0], wl[2]))
+    radindarr, radiusarr = bins_of(params)
+    rh = params['rh']
+    ang = table_angles()
+    costarr = np.cos(np.radians(ang))
+    # the file's rh coordinate is the un-capped list; the physics uses the capped one (createNCDF is called before
+    # the maxrh cap, dointegration.py:753 vs :828-832)
+    rh_used = rh
+    if 'maxrh' in params:
+        rh_used = np.array(rh)
+        rh_used[np.where(rh_used > params['maxrh'])[0]] = params['maxrh']
+    nb, nl, nr, na = len(radiusarr), len(lambarr), len(rh), len(ang)
+    vals = {}
+    for key in allkeys:
+        shape = {"scat": (nb, nl, nr, na), "ele": (nb, nl, nr, 6), "nl": (nb, nr), "scal": (nb, nl, nr)}[_kind_of(key)]
+        vals[key] = np.zeros(shape)
+
+    rank, world = (0, 1) if comm is None else (comm.rank, comm.world)
+    for radind in radindarr:
+        print("=== === === USING RADIND %d" % radind)
+        trivial = params['rhDep']['type'] == 'trivial'
+        all_cells = [(li, rhi) for li in range(nl) for rhi in range(nr) if not (trivial and rhi > 0)]
+        mine = all_cells[rank::world] if world > 1 else None
+        plan = BinPlan(params, radind, lambarr, rh_used, part_m, water_m, cells=mine)
+        mz, wp, ws, tpc = plan.tasks()
+        table = _lib.Table(plan.xx, plan.nmax, costarr)
+        scal, phase = table.run(mz, mz, wp, ws, elide=elide)
+        table.close()
+        if comm is not None and world > 1:
+            gathered = comm.gather_cells(scal, phase)
+            if rank != 0:
+                continue
+            # rank r holds all_cells[r::world]; rebuild the full bin plan metadata on rank 0
+            full = BinPlan(params, radind, lambarr, rh_used, part_m, water_m, cells=None, )
+            order = [c for r in range(world) for c in all_cells[r::world]]
+            pos = {c: i for i, c in enumerate(order)}
+            idx = np.array([pos[c] for c in full.cells])
+            tsel = (idx[:, None] * tpc + np.arange(tpc)[None, :]).reshape(-1)
+            scal, phase = gathered[0][tsel], gathered[1][tsel]
+            plan = full
+        ret = plan.reduce(scal, phase, tpc)
+        ret = postprocess(ret, ang)
+        li = np.array([c[0] for c in plan.cells])
+        ri = np.array([c[1] for c in plan.cells])
+        # mass0 = volume(RH index 0) * rhop0 of the same (bin, lambda) (dointegration.py:992-997)
+        vol0 = np.zeros(nl)
+        sel0 = ri == 0
+        vol0[li[sel0]] = ret['volume'][sel0]
+        mass0 = vol0[li] * plan.rhop0
+        ret['area'] = ret['area'] / mass0
+        ret['volume'] = ret['volume'] / mass0
+        ret['rhop'] = plan.rhop
+        ret['growth_factor'] = plan.gf
+        ret['rLow'] = plan.rLow
+        ret['rUp'] = plan.rUp
+        ret['refreal'] = plan.m[:, 0].real
+        ret['refimag'] = -np.abs(plan.m[:, 0].imag)
+        for key in allkeys:
+            kind = _kind_of(key)
+            if kind == "nl":
+                # (bin, rh) variables are overwritten at every wavelength: the last one wins (dointegration.py:1026-1027)
+                last = li == li.max()
+                vals[key][radind, ri[last]] = ret[key][last]
+            else:
+                vals[key][radind, li, ri] = ret[key]
+        if trivial:
+            # copyDryValues (dointegration.py:465-491)
+            for key in allkeys:
+                if _kind_of(key) == "nl":
+                    vals[key][radind, 1:] = vals[key][radind, 0]
+                else:
+                    vals[key][radind, :, 1:] = vals[key][radind, :, :1]
+    if rank != 0:
+        return None
+    out = {'rh': np.asarray(rh, dtype=float), 'wavelength': np.asarray(lambarr), 'ang': ang, 'vals': vals,
+           'radius': radiusarr}
+    if write:
+        write_table(partID, oppfx, out, oppclassic)
+    return out
+
+
+def write_table(ncdfID, oppfx, out, oppclassic):
+    """Write the arrays of `fun` with createNCDF's layout (new: (bin, wavelength, rh[, ang|p]); legacy:
+    (radius, rh, lambda[, ang]) and pback (nPol, radius, rh, lambda), dointegration.py:356-363, :1006-1031)."""
+    nc = createNCDF(ncdfID, oppfx, out['radius'], out['rh'], out['wavelength'], out['ang'], oppclassic)
+    for key, a in out['vals'].items():
+        kind = _kind_of(key)
+        if oppclassic:
+            if kind == "scat":
+                a = a.transpose(0, 2, 1, 3)
+            elif kind == "ele":
+                a = a.transpose(3, 0, 2, 1)
+            elif kind == "scal":
+                a = a.transpose(0, 2, 1)
+        nc.variables[key][:] = a
+    nc.close()

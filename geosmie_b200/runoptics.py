@@ -1,0 +1,73 @@
+#!/usr/bin/env python3
+"""Top-level caller for optics table generation (mirror of src/geosmie/runoptics.py; same options and file names).
+
+    python -m geosmie_b200.runoptics --name geosparticles/su.json --dest out
+    torchrun --nproc-per-node 8 -m geosmie_b200.runoptics --name geosparticles/ss.json     # cells sharded over 8 GPUs
+"""
+import os
+import shutil
+from optparse import OptionParser
+
+from . import dointegration, hydrophobic
+from . import particleparams as pp
+
+
+def main(argv=None):
+    parser = OptionParser(usage="Usage: %prog", version='0.0.1')
+    acceptedDatatypes = ['json']
+    parser.add_option("--name", dest="name", default="", help="Particle file to use (default=%s)" % (""))
+    parser.add_option("--namelist", dest="namelist", default="",
+                      help="File with list of particle files (to be passed to --file) to run iteratively. If used, overrides --file (default=%s)" % (""))
+    parser.add_option("--datatype", dest="datatype", default="json",
+                      help="Particle data type to use %s (default=%s)" % (acceptedDatatypes, "json"))
+    parser.add_option("--dest", dest="dest", default=".", help="Output directory to use (default=%s)" % ("."))
+    parser.add_option("-c", "--classic", action="store_true", dest="classic", default=False,
+                      help="write output filename is legacy dimensioning")
+    parser.add_option("--dense", action="store_true", dest="dense", default=False,
+                      help="also evaluate particles whose size-distribution weight is exactly zero (reference-equivalent work)")
+    (options, args) = parser.parse_args(argv)
+    if options.datatype not in acceptedDatatypes:
+        parser.error("data type must be one of: %s" % (acceptedDatatypes))
+    if not os.path.exists(options.dest):
+        parser.error("Output directory (--dest) does not exist")
+    if options.name == "" and options.namelist == "":
+        parser.error("non-empty particle name or namelist required (use --name particlename or --namelist namelist)")
+    namelist = []
+    if options.namelist:
+        if not os.path.exists(options.namelist):
+            parser.error("Namelist %s does not exist" % options.namelist)
+        with open(options.namelist) as fp:
+            namelist = [line.strip() for line in fp.readlines()]
+    else:
+        namelist = [options.name]
+
+    comm = None
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        from . import dist
+        comm = dist.Comm.from_env()
+    rank = 0 if comm is None else comm.rank
+
+    for fni, fn in enumerate(namelist):
+        print("Starting particle file %s, %d of %d" % (fn, fni + 1, len(namelist)))
+        if not os.path.exists(fn):
+            fn1 = "%s.json" % fn     # try with added json in case it was omitted
+            if not os.path.exists(fn1):
+                parser.error("File %s doesn't exist" % fn)
+            fn = fn1
+        params = pp.getParticleParams(fn, options.datatype)
+        particlename = fn.split('/')[-1].replace(".json", "")
+        dointegration.fun(fn, options.datatype, options.dest, options.classic, elide=not options.dense, comm=comm)
+        opfn = "optics_%s.nomom.legacy.nc4" % particlename if options.classic else "optics_%s.nomom.nc4" % particlename
+        if rank == 0 and "hydrophobic" in params and params["hydrophobic"]:
+            fn2 = "%s.nohp" % opfn
+            shutil.move(os.path.join(options.dest, opfn), os.path.join(options.dest, fn2))
+            print("Starting hydrophobic bin handling")
+            hydrophobic.doConversion(fn2, opfn, options.dest, options.classic)
+            os.remove(os.path.join(options.dest, fn2))
+        print("Done, output file: %s" % opfn)
+    if comm is not None:
+        comm.close()
+
+
+if __name__ == "__main__":
+    main()

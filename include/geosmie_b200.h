@@ -130,6 +130,12 @@ int gm_gsf_expand(gm_handle_t h, int ncell, int nang, const double* ang_deg, con
 int gm_gsf_expand_dev(gm_handle_t h, int ncell, int nang, const double* ang_deg, const double* F, int ng, double* coef,
                       double* cnorm, int quantize10);
 
+/* same expansion fed directly with gm_table_run's out_phase layout: P4 [ncell][4][nang] = P11,P12,P33,P34 (device
+ * pointers; F22 = P11, F44 = P33 for spheres, calculateScatVals dointegration.py:1044-1050).  The expansion is
+ * normalised by AL1(0), so the a-posteriori P11 normalisation of fun (:978-985, a per-cell constant) cancels. */
+int gm_gsf_expand_phase4_dev(gm_handle_t h, int ncell, int nang, const double* ang_deg, const double* P4, int ng, double* coef,
+                             double* cnorm, int quantize10);
+
 /* ---- B5: band averaging ----------------------------------------------------------------------------------------------
  * Replaces bandaverage.doAverage (src/geosmie/bandaverage.py:18-50) over all (variable, bin, rh) columns.
  *   v [ncol][nlam] at wavelengths lam[nlam] (metres, ascending); bands lo/hi [nband] in cm^-1 (use_wavenum=1) or metres
