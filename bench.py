@@ -35,30 +35,11 @@ UNIT = "particle-evals/s"
 NANG = 371
 FP64_PEAK_TFLOPS = 37.1   # measured on this pool's B200 with tools/fp64_peak.cu (DMMA m8n8k4), profiles/r01_fp64_peak.json
 
-RH36 = [0.00, 0.05, 0.10, 0.15, 0.20, 0.25, 0.30, 0.35, 0.40, 0.45, 0.50, 0.55, 0.60, 0.65, 0.70, 0.75, 0.80, 0.81, 0.82, 0.83,
-        0.84, 0.85, 0.86, 0.87, 0.88, 0.89, 0.90, 0.91, 0.92, 0.93, 0.94, 0.95, 0.96, 0.97, 0.98, 0.99]
-SU_PARAMS = {
-    "rhop0": 1700.0, "rh": RH36,
-    "rhDep": {"type": "simple", "params": {"gf": [1.00, 1.04, 1.08, 1.12, 1.16, 1.20, 1.23, 1.27, 1.31, 1.35, 1.39, 1.43, 1.46,
-                                                  1.50, 1.54, 1.59, 1.64, 1.65, 1.66, 1.67, 1.68, 1.69, 1.71, 1.72, 1.74, 1.75,
-                                                  1.77, 1.79, 1.82, 1.84, 1.87, 1.91, 1.94, 1.99, 2.05, 2.16]}},
-    "psd": {"type": "lognorm", "params": {"r0": [[0.0695e-6]], "rmin0": [[0.005e-6]], "rmax0": [[0.3e-6]], "sigma": [[2.03]],
-                                          "numperdec": [1000], "fracs": [[1.0]]}},
-}
-
 
 def build_su_plan():
     """Host inputs of the SU table exactly as dointegration.fun derives them (grid, m(lambda, RH), number weights)."""
-    from scipy.interpolate import interp1d
-    from geosmie_b200 import dointegration as DI
-    g = np.load(os.path.join(ROOT, "tests", "golden", "hostlogic.npz"))
-    ml, water = g["su__mlist"], g["su__water"]
-    lambarr = ml[0]
-    part_m = [(interp1d(ml[0], ml[1]), interp1d(ml[0], ml[2]))]
-    water_m = (interp1d(water[0], water[1]), interp1d(water[0], water[2]))
-    params = json.loads(json.dumps(SU_PARAMS))
-    plan = DI.BinPlan(params, 0, lambarr, params["rh"], part_m, water_m)
-    return plan
+    from geosmie_b200 import workloads
+    return workloads.bin_plan("su", 0)
 
 
 def flop_model(nmax, nmx_sum, ncell_factor=1):

@@ -37,7 +37,7 @@ extern "C" int gm_init(int device, gm_handle_t* out) {
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
   // opt in to the large dynamic shared memory of the contraction kernels once
-  const int smem = GM_STAGES * GM_STAGE_DBL * 8 + 2 * GM_STAGES * 8;
+  const int smem = GM_CONTRACT_SMEM;
   GM_CUDA_TRY(cudaFuncSetAttribute(k_contract<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   GM_CUDA_TRY(cudaFuncSetAttribute(k_contract<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   *out = h;
@@ -445,7 +445,8 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
     return rc;
   GM_CUDA_TRY(cudaMemcpyAsync(t->chunk_start.p, cstart.data(), sizeof(int) * (nchunk + 1), cudaMemcpyHostToDevice, st));
   GM_CUDA_TRY(cudaMemsetAsync(t->stats.p, 0, sizeof(unsigned long long) * 8, st));
-  const int smem = GM_STAGES * GM_STAGE_DBL * 8 + 2 * GM_STAGES * 8;
+  const int smem = GM_CONTRACT_SMEM;
+  GM_REQUIRE(G.ngroup <= GM_MAX_CHUNK_GROUPS, "too many particle groups per chunk (nx > 32 * GM_MAX_CHUNK_GROUPS)");
   const int64_t launches0 = h->launches;
   t->evused = 0;
 

@@ -83,6 +83,8 @@ constexpr int GM_KSTEP = 4;           // DMMA k extent
 constexpr int GM_STAGE_DBL = GM_KSTEP * GM_TROW + GM_KSTEP * GM_SB;
 constexpr int GM_STAGES = 8;
 constexpr int GM_CONTRACT_WARPS = 12;
+constexpr int GM_MAX_CHUNK_GROUPS = 4096;   // group metadata staged in shared memory per contraction CTA (nx <= 131072 per bin)
+constexpr int GM_CONTRACT_SMEM = GM_STAGES * GM_STAGE_DBL * 8 + 2 * GM_STAGES * 8 + GM_MAX_CHUNK_GROUPS * 8;
 
 // ------------------------------------------------------------------------------------------------ complex helpers
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {

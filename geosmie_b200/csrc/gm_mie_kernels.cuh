@@ -348,6 +348,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!ok);
 }
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
@@ -385,6 +394,7 @@ __global__ void __launch_bounds__(GM_CONTRACT_WARPS * 32, 1) k_contract(Contract
   double* stages = reinterpret_cast<double*>(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)GM_STAGES * GM_STAGE_DBL * 8);
   uint64_t* empty = full + GM_STAGES;
+  int2* meta = reinterpret_cast<int2*>(empty + GM_STAGES);   // per group of the chunk: (k4 steps or 0 if inactive, first row)
 
   const int item = blockIdx.x;
   const int half = item & 1;
@@ -400,38 +410,42 @@ __global__ void __launch_bounds__(GM_CONTRACT_WARPS * 32, 1) k_contract(Contract
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();
-
   const int cs = A.chunk_start[chunk], ce = A.chunk_start[chunk + 1];
-  const unsigned char* gact = A.gact + (size_t)task * A.ngroup;
+  const int ng = ce - cs;
+  {
+    const unsigned char* gact = A.gact + (size_t)task * A.ngroup;
+    for (int g = threadIdx.x; g < ng; g += blockDim.x) meta[g] = make_int2(gact[cs + g] ? A.gk4[cs + g] : 0, A.grow[cs + g]);
+  }
+  __syncthreads();
   int nsteps = 0;
-  for (int g = cs; g < ce; ++g)
-    if (gact[g]) nsteps += A.gk4[g];
+  for (int g = 0; g < ng; ++g) nsteps += meta[g].x;
 
   const double* Th = A.T + (size_t)half * A.nrows * GM_TROW;
   const double* coef_t = A.coef + (size_t)task * A.task_stride;
 
-  // producer cursor (advanced by thread 0 only)
-  int pg = cs, pk = 0, pstep = 0;
-  while (pg < ce && !gact[pg]) ++pg;
-  constexpr int LOOKAHEAD = GM_STAGES - 2;
+  // producer cursor (thread 0 only): next (group, k) to fetch
+  int pg = 0, pk = 0, pstep = 0;
+  while (pg < ng && meta[pg].x == 0) ++pg;
   constexpr uint32_t TBYTES = GM_KSTEP * GM_TROW * 8, CBYTES = GM_KSTEP * GM_SB * 8;
-  auto issue = [&]() {
-    const int s = pstep % GM_STAGES;
-    if (pstep >= GM_STAGES) mbar_wait(&empty[s], ((pstep / GM_STAGES) - 1) & 1);
-    double* dst = stages + (size_t)s * GM_STAGE_DBL;
-    mbar_expect_tx(&full[s], TBYTES + CBYTES);
-    bulk_g2s(dst, Th + (size_t)pk * GM_KSTEP * GM_TROW, TBYTES, &full[s]);
-    bulk_g2s(dst + GM_KSTEP * GM_TROW, coef_t + ((size_t)A.grow[pg] + (size_t)pk * GM_KSTEP) * GM_SB, CBYTES, &full[s]);
-    ++pstep;
-    if (++pk == A.gk4[pg]) {
-      pk = 0;
-      ++pg;
-      while (pg < ce && !gact[pg]) ++pg;
+  // fetch as many steps as there are free stages, never blocking: a stage is free once all 12 warps released its
+  // previous use (non-blocking mbarrier test), so the producer never stalls warp 0's own MMA stream
+  auto produce = [&](int consumed) {
+    while (pstep < nsteps && pstep < consumed + GM_STAGES) {
+      const int s = pstep % GM_STAGES;
+      if (pstep >= GM_STAGES && !mbar_test(&empty[s], ((pstep / GM_STAGES) - 1) & 1)) break;
+      double* dst = stages + (size_t)s * GM_STAGE_DBL;
+      mbar_expect_tx(&full[s], TBYTES + CBYTES);
+      bulk_g2s(dst, Th + (size_t)pk * GM_KSTEP * GM_TROW, TBYTES, &full[s]);
+      bulk_g2s(dst + GM_KSTEP * GM_TROW, coef_t + ((size_t)meta[pg].y + (size_t)pk * GM_KSTEP) * GM_SB, CBYTES, &full[s]);
+      ++pstep;
+      if (++pk == meta[pg].x) {
+        pk = 0;
+        ++pg;
+        while (pg < ng && meta[pg].x == 0) ++pg;
+      }
     }
   };
-  if (threadIdx.x == 0)
-    for (int s = 0; s < LOOKAHEAD && s < nsteps; ++s) issue();
+  if (threadIdx.x == 0) produce(0);
 
   double accp[2][8][2], accm[2][8][2];
 #pragma unroll
@@ -444,11 +458,12 @@ __global__ void __launch_bounds__(GM_CONTRACT_WARPS * 32, 1) k_contract(Contract
 
   const int a0 = warp * 16;
   int step = 0;
-  for (int g = cs; g < ce; ++g) {
-    if (!gact[g]) continue;
-    const int nk = A.gk4[g];
+  for (int gi = 0; gi < ng; ++gi) {
+    const int nk = meta[gi].x;
+    if (nk == 0) continue;
+    const int g = cs + gi;
     for (int k = 0; k < nk; ++k, ++step) {
-      if (threadIdx.x == 0 && step + LOOKAHEAD < nsteps) issue();
+      if (threadIdx.x == 0) produce(step);
       __syncwarp();
       const int s = step % GM_STAGES;
       mbar_wait(&full[s], (step / GM_STAGES) & 1);
