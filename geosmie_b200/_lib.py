@@ -6,7 +6,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgeosmie_b200.so")
+LIB_PATH = os.environ.get("GEOSMIE_LIB", os.path.join(_HERE, "libgeosmie_b200.so"))
 
 GM_NSCAL = 11
 S_W, S_X2W, S_X3W, S_X4W, S_QEXT, S_QSCA, S_QABS, S_QB, S_G, S_CSCA, S_CEXT = range(11)

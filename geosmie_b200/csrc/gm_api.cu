@@ -1,5 +1,6 @@
 // gm_api.cu -- host side of the C ABI declared in include/geosmie_b200.h (lifetime, per-particle Mie, table cells).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -422,8 +423,9 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
   tb = std::min(tb, ntask);
   tb = std::min(tb, 32768);  // grid.y limit of k_coeff
   // chunks: enough CTAs to fill the machine ~8x over, cost-balanced by k4 steps
-  const int want_items = 8 * h->sm_count;
+  const int want_items = GM_WANT_ITEMS_CFG * h->sm_count;   // equal-cost CTAs per SM: bounds the last-wave tail
   int nchunk = (want_items + 2 * tb - 1) / (2 * tb);
+  nchunk = std::max(nchunk, (G.ngroup + GM_MAX_CHUNK_GROUPS / 2 - 1) / (GM_MAX_CHUNK_GROUPS / 2));   // chunk metadata must fit in smem
   nchunk = std::max(1, std::min(nchunk, G.ngroup));
   std::vector<int> cstart(nchunk + 1, 0);
   {
@@ -446,7 +448,8 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
   GM_CUDA_TRY(cudaMemcpyAsync(t->chunk_start.p, cstart.data(), sizeof(int) * (nchunk + 1), cudaMemcpyHostToDevice, st));
   GM_CUDA_TRY(cudaMemsetAsync(t->stats.p, 0, sizeof(unsigned long long) * 8, st));
   const int smem = GM_CONTRACT_SMEM;
-  GM_REQUIRE(G.ngroup <= GM_MAX_CHUNK_GROUPS, "too many particle groups per chunk (nx > 32 * GM_MAX_CHUNK_GROUPS)");
+  for (int c = 0; c < nchunk; ++c)
+    GM_REQUIRE(cstart[c + 1] - cstart[c] <= GM_MAX_CHUNK_GROUPS, "chunk has more particle groups than the smem metadata holds");
   const int64_t launches0 = h->launches;
   t->evused = 0;
 

@@ -81,21 +81,42 @@ constexpr int GM_TROW = 2 * GM_LAH;   // p_n row then q_n row
 constexpr int GM_SB = 132;            // doubles per coefficient row: 64 (c+) + 64 (c-) + 4 pad (stride 4 mod 16 -> conflict-free B fragments)
 constexpr int GM_KSTEP = 4;           // DMMA k extent
 constexpr int GM_STAGE_DBL = GM_KSTEP * GM_TROW + GM_KSTEP * GM_SB;
-constexpr int GM_STAGES = 8;
+#ifndef GM_EARLY_TEST
+#define GM_EARLY_TEST 0
+#endif
+#ifndef GM_WANT_ITEMS_CFG
+#define GM_WANT_ITEMS_CFG 32
+#endif
+#ifndef GM_SPS_CFG
+#define GM_SPS_CFG 1
+#endif
+#ifndef GM_STAGES_CFG
+#define GM_STAGES_CFG 8
+#endif
+constexpr int GM_SPS = GM_SPS_CFG;        // k4 steps per pipeline stage (one mbarrier round trip per stage)
+constexpr int GM_STAGES = GM_STAGES_CFG;  // pipeline stages
 constexpr int GM_CONTRACT_WARPS = 12;
-constexpr int GM_MAX_CHUNK_GROUPS = 4096;   // group metadata staged in shared memory per contraction CTA (nx <= 131072 per bin)
-constexpr int GM_CONTRACT_SMEM = GM_STAGES * GM_STAGE_DBL * 8 + 2 * GM_STAGES * 8 + GM_MAX_CHUNK_GROUPS * 8;
+constexpr int GM_MAX_CHUNK_GROUPS = 1024;   // group metadata staged in shared memory per contraction CTA
+constexpr int GM_CONTRACT_SMEM = GM_STAGES * GM_SPS * GM_STAGE_DBL * 8 + 2 * GM_STAGES * 8 + GM_MAX_CHUNK_GROUPS * 8;
 
 // ------------------------------------------------------------------------------------------------ complex helpers
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
   return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
 }
+// reciprocal of a normal, finite double: MUFU.RCP64H seed (~20 bits) + two Newton steps (<= 1 ulp), no slow path
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  return r;
+}
 __device__ __forceinline__ double2 crcp(double2 b) {
-  double inv = 1.0 / fma(b.x, b.x, b.y * b.y);
+  double inv = fast_rcp(fma(b.x, b.x, b.y * b.y));
   return make_double2(b.x * inv, -b.y * inv);
 }
 __device__ __forceinline__ double2 cdiv(double2 a, double2 b) {
-  double inv = 1.0 / fma(b.x, b.x, b.y * b.y);
+  double inv = fast_rcp(fma(b.x, b.x, b.y * b.y));
   return make_double2(fma(a.x, b.x, a.y * b.y) * inv, fma(a.y, b.x, -a.x * b.y) * inv);
 }
 __device__ __forceinline__ double warp_sum(double v) {

@@ -162,7 +162,7 @@ struct CoeffArgs {
 
 // MODE 0: DMMA group layout (c+ = (a+b) f_n sqrt(w), c- = (a-b) f_n sqrt(w)); MODE 1: natural a_n, b_n.
 template <int MODE>
-__global__ void __launch_bounds__(128) k_coeff(CoeffArgs A) {
+__global__ void __launch_bounds__(128, 4) k_coeff(CoeffArgs A) {
   const int g = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (g >= A.ngroup) return;
   const int lane = threadIdx.x & 31;
@@ -211,6 +211,12 @@ __global__ void __launch_bounds__(128) k_coeff(CoeffArgs A) {
   double psi_n = 0.0, chi_n = 0.0;
   double2 a_next = make_double2(0.0, 0.0), b_next = make_double2(0.0, 0.0);
   double sext = 0.0, ssca = 0.0, qbr = 0.0, qbi = 0.0, sasy = 0.0;
+  // Riccati-Bessel values are prefetched PD orders ahead of their use (the table read is the only memory access on
+  // the serial recurrence's critical path)
+  constexpr int PD = 4;
+  double qpsi[PD], qchi[PD];
+#pragma unroll
+  for (int k = 0; k < PD; ++k) qpsi[k] = qchi[k] = 0.0;
 
   int nstart = J - 1;
   if (MODE == 0 && rows > nstart) nstart = rows;
@@ -221,14 +227,28 @@ __global__ void __launch_bounds__(128) k_coeff(CoeffArgs A) {
       const double2 ti = crcp(make_double2(D.x + r.x, D.y + r.y));
       D = make_double2(r.x - ti.x, r.y - ti.y);
     }
+    if (act && n == nm + 8) {                                // nmx >= nmax + 16, so this iteration always exists
+      psi_n = A.psi[bbase + (size_t)nm * 32];
+      chi_n = A.chi[bbase + (size_t)nm * 32];
+#pragma unroll
+      for (int k = 0; k < PD; ++k)
+        if (nm - 1 - k >= 0) {
+          qpsi[k] = A.psi[bbase + (size_t)(nm - 1 - k) * 32];
+          qchi[k] = A.chi[bbase + (size_t)(nm - 1 - k) * 32];
+        }
+    }
     double2 cp = make_double2(0.0, 0.0), cm = make_double2(0.0, 0.0);
     if (act && n <= nm) {
-      if (n == nm) {
-        psi_n = A.psi[bbase + (size_t)n * 32];
-        chi_n = A.chi[bbase + (size_t)n * 32];
+      const double psi_m = qpsi[0], chi_m = qchi[0];        // order n-1
+#pragma unroll
+      for (int k = 0; k + 1 < PD; ++k) {
+        qpsi[k] = qpsi[k + 1];
+        qchi[k] = qchi[k + 1];
       }
-      const double psi_m = A.psi[bbase + (size_t)(n - 1) * 32];
-      const double chi_m = A.chi[bbase + (size_t)(n - 1) * 32];
+      if (n - 1 - PD >= 0) {
+        qpsi[PD - 1] = A.psi[bbase + (size_t)(n - 1 - PD) * 32];
+        qchi[PD - 1] = A.chi[bbase + (size_t)(n - 1 - PD) * 32];
+      }
       const double dn = (double)n;
       const double nox = dn * xinv;
       double2 da = cmul(D, minv);                             // mie_coeffs.py:124
@@ -392,7 +412,7 @@ template <bool PER_PARTICLE>
 __global__ void __launch_bounds__(GM_CONTRACT_WARPS * 32, 1) k_contract(ContractArgs A) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* stages = reinterpret_cast<double*>(smem_raw);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)GM_STAGES * GM_STAGE_DBL * 8);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)GM_STAGES * GM_SPS * GM_STAGE_DBL * 8);
   uint64_t* empty = full + GM_STAGES;
   int2* meta = reinterpret_cast<int2*>(empty + GM_STAGES);   // per group of the chunk: (k4 steps or 0 if inactive, first row)
 
@@ -423,26 +443,31 @@ __global__ void __launch_bounds__(GM_CONTRACT_WARPS * 32, 1) k_contract(Contract
   const double* Th = A.T + (size_t)half * A.nrows * GM_TROW;
   const double* coef_t = A.coef + (size_t)task * A.task_stride;
 
-  // producer cursor (thread 0 only): next (group, k) to fetch
-  int pg = 0, pk = 0, pstep = 0;
+  // producer cursor (thread 0 only): next (group, k) to fetch.  A stage holds GM_SPS consecutive k4 steps and has one
+  // full / one empty mbarrier, so the consumers pay one barrier round trip per GM_SPS steps.
+  int pg = 0, pk = 0, pstage = 0;
   while (pg < ng && meta[pg].x == 0) ++pg;
+  const int nstages = (nsteps + GM_SPS - 1) / GM_SPS;
   constexpr uint32_t TBYTES = GM_KSTEP * GM_TROW * 8, CBYTES = GM_KSTEP * GM_SB * 8;
-  // fetch as many steps as there are free stages, never blocking: a stage is free once all 12 warps released its
-  // previous use (non-blocking mbarrier test), so the producer never stalls warp 0's own MMA stream
-  auto produce = [&](int consumed) {
-    while (pstep < nsteps && pstep < consumed + GM_STAGES) {
-      const int s = pstep % GM_STAGES;
-      if (pstep >= GM_STAGES && !mbar_test(&empty[s], ((pstep / GM_STAGES) - 1) & 1)) break;
-      double* dst = stages + (size_t)s * GM_STAGE_DBL;
-      mbar_expect_tx(&full[s], TBYTES + CBYTES);
-      bulk_g2s(dst, Th + (size_t)pk * GM_KSTEP * GM_TROW, TBYTES, &full[s]);
-      bulk_g2s(dst + GM_KSTEP * GM_TROW, coef_t + ((size_t)meta[pg].y + (size_t)pk * GM_KSTEP) * GM_SB, CBYTES, &full[s]);
-      ++pstep;
-      if (++pk == meta[pg].x) {
-        pk = 0;
-        ++pg;
-        while (pg < ng && meta[pg].x == 0) ++pg;
+  // fetch as many stages as are free, never blocking: a stage is free once all 12 warps released its previous use
+  // (non-blocking mbarrier test), so the producer never stalls warp 0's own MMA stream
+  auto produce = [&](int consumed_stage) {
+    while (pstage < nstages && pstage < consumed_stage + GM_STAGES) {
+      const int s = pstage % GM_STAGES;
+      if (pstage >= GM_STAGES && !mbar_test(&empty[s], ((pstage / GM_STAGES) - 1) & 1)) break;
+      const int nsub = min(GM_SPS, nsteps - pstage * GM_SPS);
+      mbar_expect_tx(&full[s], (uint32_t)nsub * (TBYTES + CBYTES));
+      for (int u = 0; u < nsub; ++u) {
+        double* dst = stages + ((size_t)s * GM_SPS + u) * GM_STAGE_DBL;
+        bulk_g2s(dst, Th + (size_t)pk * GM_KSTEP * GM_TROW, TBYTES, &full[s]);
+        bulk_g2s(dst + GM_KSTEP * GM_TROW, coef_t + ((size_t)meta[pg].y + (size_t)pk * GM_KSTEP) * GM_SB, CBYTES, &full[s]);
+        if (++pk == meta[pg].x) {
+          pk = 0;
+          ++pg;
+          while (pg < ng && meta[pg].x == 0) ++pg;
+        }
       }
+      ++pstage;
     }
   };
   if (threadIdx.x == 0) produce(0);
@@ -458,15 +483,22 @@ __global__ void __launch_bounds__(GM_CONTRACT_WARPS * 32, 1) k_contract(Contract
 
   const int a0 = warp * 16;
   int step = 0;
+#if GM_EARLY_TEST
+  bool ready = false;   // full barrier of the current step already observed complete (tested one step early)
+#endif
   for (int gi = 0; gi < ng; ++gi) {
     const int nk = meta[gi].x;
     if (nk == 0) continue;
     const int g = cs + gi;
     for (int k = 0; k < nk; ++k, ++step) {
+      const int s = step % GM_STAGES;
+#if GM_EARLY_TEST
+      if (!ready) mbar_wait(&full[s], (step / GM_STAGES) & 1);
+#else
       if (threadIdx.x == 0) produce(step);
       __syncwarp();
-      const int s = step % GM_STAGES;
       mbar_wait(&full[s], (step / GM_STAGES) & 1);
+#endif
       const double* tb = stages + (size_t)s * GM_STAGE_DBL + lk * GM_TROW + a0 + lr;
       const double* cf = stages + (size_t)s * GM_STAGE_DBL + GM_KSTEP * GM_TROW + lk * GM_SB + lr;
       double ap[2], aq[2];
@@ -475,6 +507,11 @@ __global__ void __launch_bounds__(GM_CONTRACT_WARPS * 32, 1) k_contract(Contract
         ap[i] = tb[8 * i];
         aq[i] = tb[GM_LAH + 8 * i];
       }
+#if GM_EARLY_TEST
+      // next step's full barrier is tested here (non-blocking); the result is only consumed after the 32 DMMAs
+      const int nx_s = (step + 1) % GM_STAGES;
+      const bool ok = (step + 1 < nsteps) && mbar_test(&full[nx_s], ((step + 1) / GM_STAGES) & 1);
+#endif
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const double bp = cf[8 * j];
@@ -487,6 +524,10 @@ __global__ void __launch_bounds__(GM_CONTRACT_WARPS * 32, 1) k_contract(Contract
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
+#if GM_EARLY_TEST
+      if (threadIdx.x == 0) produce(step + 1);
+      ready = __all_sync(0xffffffffu, ok);
+#endif
     }
     // group epilogue
 #pragma unroll
