@@ -211,14 +211,15 @@ def main():
             torch.cat([scal_d.reshape(ncell, -1), phase_d.reshape(ncell, -1), coef_d.reshape(ncell, -1)], dim=1, out=packed)
             td.gather(packed, gather_buf, dst=0)
 
+    mz_hn, w_hn = mz_h.numpy(), w_h.numpy()          # views of the pinned host buffers
+    scal_hn, phase_hn = scal_h.numpy(), phase_h.numpy()
+
     def step_e2e():
-        # the user-facing call with HOST buffers: H2D of this step's inputs, kernels, D2H of the results
-        mzd = mz_h.to(dev, non_blocking=True)
-        wd = w_h.to(dev, non_blocking=True)
-        table.run_dev(ncell, mzd.data_ptr(), mzd.data_ptr(), 1, wd.data_ptr(), 0, scal_d.data_ptr(), phase_d.data_ptr(), elide=False)
-        h.gsf_expand_phase4_dev(ang, ncell, phase_d.data_ptr(), coef_d.data_ptr(), cn_d.data_ptr())
-        scal_h.copy_(scal_d, non_blocking=True)
-        phase_h.copy_(phase_d, non_blocking=True)
+        # the user-facing call with HOST buffers (gm_table_run): H2D of this step's inputs, kernels and D2H of the results,
+        # pipelined batch by batch inside the library; then the GSF expansion of the device copy and D2H of the moments
+        table.run_into(ncell, mz_hn, mz_hn, w_hn, scal_hn, phase_hn, elide=False)
+        _, ph_ptr = table.device_outputs()
+        h.gsf_expand_phase4_dev(ang, ncell, ph_ptr, coef_d.data_ptr(), cn_d.data_ptr())
         coef_h.copy_(coef_d, non_blocking=True)
         if world > 1:
             torch.cat([scal_d.reshape(ncell, -1), phase_d.reshape(ncell, -1), coef_d.reshape(ncell, -1)], dim=1, out=packed)

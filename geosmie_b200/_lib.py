@@ -37,6 +37,7 @@ SIGNATURES = {
     "gm_table_set_bessel": (C.c_int, [vp, vp, vp, vp]),
     "gm_table_run": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int, vp, vp]),
     "gm_table_run_dev": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int, vp, vp]),
+    "gm_table_device_outputs": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp)]),
     "gm_table_particles": (C.c_int, [vp, C.c_int, vp, vp, vp, vp]),
     "gm_table_last_stats": (C.c_int, [vp, vp]),
     "gm_table_set_timing": (C.c_int, [vp, C.c_int]),
@@ -219,6 +220,16 @@ class Table:
         check(self.lib.gm_table_run(self.t, ntask, ptr(mz), ptr(mrel), nmode, ptr(wp), ptr(ws), F_ELIDE_ZERO_WEIGHT if elide else 0,
                                     ptr(scal), ptr(phase)))
         return scal, phase
+
+    def run_into(self, ntask, mz, mrel, w_phase, scal_out, phase_out, elide=False):
+        """Host-buffer call writing into caller-provided (ideally pinned) numpy arrays; single-mode weights."""
+        check(self.lib.gm_table_run(self.t, ntask, ptr(mz), ptr(mrel), 1, ptr(w_phase), None, F_ELIDE_ZERO_WEIGHT if elide else 0,
+                                    ptr(scal_out), ptr(phase_out)))
+
+    def device_outputs(self):
+        a, b = vp(), vp()
+        check(self.lib.gm_table_device_outputs(self.t, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def run_dev(self, ntask, mz_ptr, mrel_ptr, nmode, wphase_ptr, wscal_ptr, out_scal_ptr, out_phase_ptr, elide=False):
         """Device-pointer call (asynchronous on the handle's stream); pointers are integers (tensor.data_ptr())."""

@@ -275,6 +275,8 @@ struct gm_table_s {
   DevBuf coef, gact, scal_part, part, chunk_start, mz, mrel, wphase, wscal, out_scal, out_phase, stats, q, s12;
   double last_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int timing = 0;
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // host-buffer calls: copies pipelined against the kernels
+  std::vector<cudaEvent_t> io_events;
   std::vector<cudaEvent_t> evpool;   // pairs of events recorded around every launch of the last run (timing mode)
   std::vector<int> evkind;           // 0 coeff, 1 contract, 2 finalize
   size_t evused = 0;
@@ -324,6 +326,9 @@ extern "C" int gm_table_destroy(gm_table_t t) {
                     &t->wscal, &t->out_scal, &t->out_phase, &t->stats, &t->q, &t->s12})
     b->release();
   for (auto& e : t->evpool) cudaEventDestroy(e);
+  for (auto& e : t->io_events) cudaEventDestroy(e);
+  if (t->h2d_stream) cudaStreamDestroy(t->h2d_stream);
+  if (t->d2h_stream) cudaStreamDestroy(t->d2h_stream);
   delete t;
   return GM_OK;
 }
@@ -409,10 +414,20 @@ extern "C" int gm_table_last_stats(gm_table_t t, double stats[8]) {
   return GM_OK;
 }
 
+// host buffers of a gm_table_run call whose transfers are pipelined batch by batch against the kernels
+struct HostIO {
+  const double* w_phase;
+  const double* w_scal;
+  double* out_scal;
+  double* out_phase;
+};
+
 // Core of gm_table_run: all pointers are DEVICE pointers.  per_particle != 0 selects the S1/S2-per-particle epilogue.
+// With `hio`, the weights of batch b are uploaded on a copy stream while batch b-1 computes, and the results of batch b
+// are downloaded while batch b+1 computes.
 static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const double* d_mrel, int nmode, const double* d_wphase,
                           const double* d_wscal, int flags, double* d_out_scal, double* d_out_phase, double* d_q, double* d_s12,
-                          bool per_particle) {
+                          bool per_particle, const HostIO* hio = nullptr) {
   gm_handle_t h = t->h;
   cudaStream_t st = h->stream;
   const Groups& G = t->G;
@@ -422,6 +437,7 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
   int tb = (int)std::max<size_t>(1, h->coef_budget_bytes / std::max<size_t>(per_task_bytes, 1));
   tb = std::min(tb, ntask);
   tb = std::min(tb, 32768);  // grid.y limit of k_coeff
+  if (hio && ntask >= 256) tb = std::min(tb, (ntask + 3) / 4);   // at least 4 batches so that copies overlap compute
   // chunks: enough CTAs to fill the machine ~8x over, cost-balanced by k4 steps
   const int want_items = GM_WANT_ITEMS_CFG * h->sm_count;   // equal-cost CTAs per SM: bounds the last-wave tail
   int nchunk = (want_items + 2 * tb - 1) / (2 * tb);
@@ -452,9 +468,36 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
     GM_REQUIRE(cstart[c + 1] - cstart[c] <= GM_MAX_CHUNK_GROUPS, "chunk has more particle groups than the smem metadata holds");
   const int64_t launches0 = h->launches;
   t->evused = 0;
+  const int nbatch = (ntask + tb - 1) / tb;
+  if (hio) {
+    if (!t->h2d_stream) {
+      GM_CUDA_TRY(cudaStreamCreateWithFlags(&t->h2d_stream, cudaStreamNonBlocking));
+      GM_CUDA_TRY(cudaStreamCreateWithFlags(&t->d2h_stream, cudaStreamNonBlocking));
+    }
+    while ((int)t->io_events.size() < 2 * nbatch + 1) {
+      cudaEvent_t e;
+      GM_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      t->io_events.push_back(e);
+    }
+    // the copy streams must not run ahead of work already queued on the compute stream (buffers are reused between calls)
+    GM_CUDA_TRY(cudaEventRecord(t->io_events[2 * nbatch], st));
+    GM_CUDA_TRY(cudaStreamWaitEvent(t->h2d_stream, t->io_events[2 * nbatch], 0));
+    GM_CUDA_TRY(cudaStreamWaitEvent(t->d2h_stream, t->io_events[2 * nbatch], 0));
+    for (int b = 0; b < nbatch; ++b) {
+      const int t0 = b * tb, nt = std::min(tb, ntask - t0);
+      GM_CUDA_TRY(cudaMemcpyAsync(const_cast<double*>(d_wphase) + (size_t)t0 * G.nx, hio->w_phase + (size_t)t0 * G.nx,
+                                  sizeof(double) * (size_t)nt * G.nx, cudaMemcpyHostToDevice, t->h2d_stream));
+      if (hio->w_scal)
+        GM_CUDA_TRY(cudaMemcpyAsync(const_cast<double*>(d_wscal) + (size_t)t0 * nmode * G.nx, hio->w_scal + (size_t)t0 * nmode * G.nx,
+                                    sizeof(double) * (size_t)nt * nmode * G.nx, cudaMemcpyHostToDevice, t->h2d_stream));
+      GM_CUDA_TRY(cudaEventRecord(t->io_events[b], t->h2d_stream));
+    }
+  }
 
   for (int t0 = 0; t0 < ntask; t0 += tb) {
     const int nt = std::min(tb, ntask - t0);
+    const int bi = t0 / tb;
+    if (hio) GM_CUDA_TRY(cudaStreamWaitEvent(st, t->io_events[bi], 0));
     CoeffArgs A;
     memset(&A, 0, sizeof(A));
     A.nx = G.nx;
@@ -515,9 +558,21 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
                                              d_out_phase + (size_t)t0 * 4 * t->nang, d_out_scal + (size_t)t0 * nmode * GM_NSCAL);
       GM_LAUNCH_CHECK(h);
       if ((rc = ev_mark(t, 2))) return rc;
+      if (hio) {
+        GM_CUDA_TRY(cudaEventRecord(t->io_events[nbatch + bi], st));
+        GM_CUDA_TRY(cudaStreamWaitEvent(t->d2h_stream, t->io_events[nbatch + bi], 0));
+        GM_CUDA_TRY(cudaMemcpyAsync(hio->out_scal + (size_t)t0 * nmode * GM_NSCAL, d_out_scal + (size_t)t0 * nmode * GM_NSCAL,
+                                    sizeof(double) * (size_t)nt * nmode * GM_NSCAL, cudaMemcpyDeviceToHost, t->d2h_stream));
+        GM_CUDA_TRY(cudaMemcpyAsync(hio->out_phase + (size_t)t0 * 4 * t->nang, d_out_phase + (size_t)t0 * 4 * t->nang,
+                                    sizeof(double) * (size_t)nt * 4 * t->nang, cudaMemcpyDeviceToHost, t->d2h_stream));
+      }
     }
   }
   t->last_stats[4] = (double)(h->launches - launches0);
+  if (hio) {
+    GM_CUDA_TRY(cudaStreamSynchronize(t->d2h_stream));
+    GM_CUDA_TRY(cudaStreamSynchronize(t->h2d_stream));
+  }
   return GM_OK;
 }
 
@@ -557,15 +612,20 @@ extern "C" int gm_table_run(gm_table_t t, int ntask, const double* mz, const dou
   if (w_scal && (rc = t->wscal.ensure(sizeof(double) * nw * nmode))) return rc;
   GM_CUDA_TRY(cudaMemcpyAsync(t->mz.p, mz, sizeof(double2) * ntask, cudaMemcpyHostToDevice, st));
   GM_CUDA_TRY(cudaMemcpyAsync(t->mrel.p, mrel, sizeof(double2) * ntask, cudaMemcpyHostToDevice, st));
-  GM_CUDA_TRY(cudaMemcpyAsync(t->wphase.p, w_phase, sizeof(double) * nw, cudaMemcpyHostToDevice, st));
-  if (w_scal) GM_CUDA_TRY(cudaMemcpyAsync(t->wscal.p, w_scal, sizeof(double) * nw * nmode, cudaMemcpyHostToDevice, st));
+  HostIO hio = {w_phase, w_scal, out_scal, out_phase};
   rc = table_run_core(t, ntask, t->mz.as<double>(), t->mrel.as<double>(), nmode, t->wphase.as<double>(),
                       w_scal ? t->wscal.as<double>() : nullptr, flags, t->out_scal.as<double>(), t->out_phase.as<double>(), nullptr,
-                      nullptr, false);
+                      nullptr, false, &hio);
   if (rc) return rc;
-  GM_CUDA_TRY(cudaMemcpyAsync(out_scal, t->out_scal.p, sizeof(double) * (size_t)ntask * nmode * GM_NSCAL, cudaMemcpyDeviceToHost, st));
-  GM_CUDA_TRY(cudaMemcpyAsync(out_phase, t->out_phase.p, sizeof(double) * (size_t)ntask * 4 * t->nang, cudaMemcpyDeviceToHost, st));
   return fetch_stats(t);
+}
+
+// device copies of the outputs of the last gm_table_run (host-buffer variant), e.g. to chain gm_gsf_expand_phase4_dev
+extern "C" int gm_table_device_outputs(gm_table_t t, double** out_scal, double** out_phase) {
+  GM_REQUIRE(t != nullptr, "table is NULL");
+  if (out_scal) *out_scal = t->out_scal.as<double>();
+  if (out_phase) *out_phase = t->out_phase.as<double>();
+  return GM_OK;
 }
 
 extern "C" int gm_table_particles(gm_table_t t, int ntask, const double* mz, const double* mrel, double* q, double* s12) {

@@ -81,6 +81,12 @@ constexpr int GM_TROW = 2 * GM_LAH;   // p_n row then q_n row
 constexpr int GM_SB = 132;            // doubles per coefficient row: 64 (c+) + 64 (c-) + 4 pad (stride 4 mod 16 -> conflict-free B fragments)
 constexpr int GM_KSTEP = 4;           // DMMA k extent
 constexpr int GM_STAGE_DBL = GM_KSTEP * GM_TROW + GM_KSTEP * GM_SB;
+#ifndef GM_X_NOEMPTY
+#define GM_X_NOEMPTY 0
+#endif
+#ifndef GM_X_NOFULL
+#define GM_X_NOFULL 0
+#endif
 #ifndef GM_EARLY_TEST
 #define GM_EARLY_TEST 0
 #endif

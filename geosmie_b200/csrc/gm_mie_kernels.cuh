@@ -162,7 +162,7 @@ struct CoeffArgs {
 
 // MODE 0: DMMA group layout (c+ = (a+b) f_n sqrt(w), c- = (a-b) f_n sqrt(w)); MODE 1: natural a_n, b_n.
 template <int MODE>
-__global__ void __launch_bounds__(128, 4) k_coeff(CoeffArgs A) {
+__global__ void __launch_bounds__(128, 3) k_coeff(CoeffArgs A) {
   const int g = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (g >= A.ngroup) return;
   const int lane = threadIdx.x & 31;
@@ -211,31 +211,44 @@ __global__ void __launch_bounds__(128, 4) k_coeff(CoeffArgs A) {
   double psi_n = 0.0, chi_n = 0.0;
   double2 a_next = make_double2(0.0, 0.0), b_next = make_double2(0.0, 0.0);
   double sext = 0.0, ssca = 0.0, qbr = 0.0, qbi = 0.0, sasy = 0.0;
-  // Riccati-Bessel values are prefetched PD orders ahead of their use (the table read is the only memory access on
-  // the serial recurrence's critical path)
+  // Riccati-Bessel values are fetched PD orders ahead of their use (the table read is the only memory access on the
+  // serial recurrence's critical path); the first PD+1 orders are requested before the recurrence starts.
   constexpr int PD = 4;
   double qpsi[PD], qchi[PD];
 #pragma unroll
   for (int k = 0; k < PD; ++k) qpsi[k] = qchi[k] = 0.0;
+  if (act) {
+    psi_n = A.psi[bbase + (size_t)nm * 32];
+    chi_n = A.chi[bbase + (size_t)nm * 32];
+#pragma unroll
+    for (int k = 0; k < PD; ++k)
+      if (nm - 1 - k >= 0) {
+        qpsi[k] = A.psi[bbase + (size_t)(nm - 1 - k) * 32];
+        qchi[k] = A.chi[bbase + (size_t)(nm - 1 - k) * 32];
+      }
+  }
 
+  // ---- phase 1: orders above every particle of the group: only the logarithmic-derivative recurrence
+  // mie_coeffs.py:119-121, D_n = r - 1/(D_{n+1} + r), r = (n+1)/z, started from D_{nmx} = 0
   int nstart = J - 1;
-  if (MODE == 0 && rows > nstart) nstart = rows;
-  for (int n = nstart; n >= 1; --n) {
-    if (n < nmx) {                                           // mie_coeffs.py:119-121, D_n = r - 1/(D_{n+1} + r), r = (n+1)/z
+  const int nemit = (MODE == 0) ? rows : __reduce_max_sync(0xffffffffu, act ? nm : 0);
+  if (nemit > nstart) nstart = nemit;
+  int n = nstart;
+  for (; n > nemit; --n) {
+    if (n < nmx) {
       const double f = (double)(n + 1);
       const double2 r = make_double2(f * zinv.x, f * zinv.y);
       const double2 ti = crcp(make_double2(D.x + r.x, D.y + r.y));
       D = make_double2(r.x - ti.x, r.y - ti.y);
     }
-    if (act && n == nm + 8) {                                // nmx >= nmax + 16, so this iteration always exists
-      psi_n = A.psi[bbase + (size_t)nm * 32];
-      chi_n = A.chi[bbase + (size_t)nm * 32];
-#pragma unroll
-      for (int k = 0; k < PD; ++k)
-        if (nm - 1 - k >= 0) {
-          qpsi[k] = A.psi[bbase + (size_t)(nm - 1 - k) * 32];
-          qchi[k] = A.chi[bbase + (size_t)(nm - 1 - k) * 32];
-        }
+  }
+  // ---- phase 2: orders that emit coefficients
+  for (; n >= 1; --n) {
+    if (n < nmx) {
+      const double f = (double)(n + 1);
+      const double2 r = make_double2(f * zinv.x, f * zinv.y);
+      const double2 ti = crcp(make_double2(D.x + r.x, D.y + r.y));
+      D = make_double2(r.x - ti.x, r.y - ti.y);
     }
     double2 cp = make_double2(0.0, 0.0), cm = make_double2(0.0, 0.0);
     if (act && n <= nm) {
@@ -262,13 +275,14 @@ __global__ void __launch_bounds__(128, 4) k_coeff(CoeffArgs A) {
                               make_double2(fma(db.x, psi_n, fma(db.y, chi_n, -psi_m)), fma(db.y, psi_n, fma(-db.x, chi_n, chi_m))));
       // efficiencies, mie_props.py:41-65
       const double cn = 2.0 * dn + 1.0;
+      const double rn1 = fast_rcp(dn + 1.0);
+      const double c2n = cn * rn1 * fast_rcp(dn);             // (2n+1)/(n(n+1))
       sext += cn * (an.x + bn.x);
       ssca += cn * (an.x * an.x + an.y * an.y + bn.x * bn.x + bn.y * bn.y);
       const double sg = (n & 1) ? -cn : cn;
       qbr += sg * (an.x - bn.x);
       qbi += sg * (an.y - bn.y);
-      const double c2n = cn / (dn * (dn + 1.0));
-      sasy += dn * (dn + 2.0) / (dn + 1.0) * (an.x * a_next.x + an.y * a_next.y + bn.x * b_next.x + bn.y * b_next.y) +
+      sasy += dn * (dn + 2.0) * rn1 * (an.x * a_next.x + an.y * a_next.y + bn.x * b_next.x + bn.y * b_next.y) +
               c2n * (an.x * bn.x + an.y * bn.y);
       a_next = an;
       b_next = bn;
@@ -282,7 +296,7 @@ __global__ void __launch_bounds__(128, 4) k_coeff(CoeffArgs A) {
         A.ab[abo + n - 1] = make_double4(an.x, an.y, bn.x, bn.y);
       }
     }
-    if (MODE == 0 && n <= rows) {
+    if (MODE == 0) {
       double* r = crow + (size_t)(n - 1) * GM_SB;
       *reinterpret_cast<double2*>(r) = cp;
       *reinterpret_cast<double2*>(r + 64) = cm;
@@ -454,7 +468,9 @@ __global__ void __launch_bounds__(GM_CONTRACT_WARPS * 32, 1) k_contract(Contract
   auto produce = [&](int consumed_stage) {
     while (pstage < nstages && pstage < consumed_stage + GM_STAGES) {
       const int s = pstage % GM_STAGES;
+#if !GM_X_NOEMPTY
       if (pstage >= GM_STAGES && !mbar_test(&empty[s], ((pstage / GM_STAGES) - 1) & 1)) break;
+#endif
       const int nsub = min(GM_SPS, nsteps - pstage * GM_SPS);
       mbar_expect_tx(&full[s], (uint32_t)nsub * (TBYTES + CBYTES));
       for (int u = 0; u < nsub; ++u) {
@@ -497,7 +513,9 @@ __global__ void __launch_bounds__(GM_CONTRACT_WARPS * 32, 1) k_contract(Contract
 #else
       if (threadIdx.x == 0) produce(step);
       __syncwarp();
+#if !GM_X_NOFULL
       mbar_wait(&full[s], (step / GM_STAGES) & 1);
+#endif
 #endif
       const double* tb = stages + (size_t)s * GM_STAGE_DBL + lk * GM_TROW + a0 + lr;
       const double* cf = stages + (size_t)s * GM_STAGE_DBL + GM_KSTEP * GM_TROW + lk * GM_SB + lr;
@@ -522,8 +540,10 @@ __global__ void __launch_bounds__(GM_CONTRACT_WARPS * 32, 1) k_contract(Contract
           dmma884(accm[i][j][0], accm[i][j][1], aq[i], bm);
         }
       }
+#if !GM_X_NOEMPTY
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
+#endif
 #if GM_EARLY_TEST
       if (threadIdx.x == 0) produce(step + 1);
       ready = __all_sync(0xffffffffu, ok);

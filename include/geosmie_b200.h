@@ -103,11 +103,15 @@ int gm_table_set_bessel(gm_table_t t, const int64_t* off, const double* jv_half,
  *   out_scal [ntask][nmode][GM_NSCAL]
  *   out_phase [ntask][4][nang]  sum_x w P(x,theta) for P11(=P22), P12, P33(=P44), P34
  * Deterministic: fixed reduction order, bitwise identical results run to run.
+ * The host-buffer variant pipelines its transfers batch by batch against the kernels (pass pinned memory to benefit).
  */
 int gm_table_run(gm_table_t t, int ntask, const double* mz, const double* mrel, int nmode, const double* w_phase,
                  const double* w_scal, int flags, double* out_scal, double* out_phase);
 int gm_table_run_dev(gm_table_t t, int ntask, const double* mz, const double* mrel, int nmode, const double* w_phase,
                      const double* w_scal, int flags, double* out_scal, double* out_phase);
+/* device copies of the outputs of the last host-buffer gm_table_run (valid until the next call on this table), so that
+ * gm_gsf_expand_phase4_dev can be chained without a host round trip */
+int gm_table_device_outputs(gm_table_t t, double** out_scal, double** out_phase);
 /* per-particle outputs through the table (DMMA) path: q [ntask][nx][6], s12 [ntask][nx][nang][4] (host pointers) */
 int gm_table_particles(gm_table_t t, int ntask, const double* mz, const double* mrel, double* q, double* s12);
 /* statistics of the last gm_table_run*: [0] particle evaluations, [1] sum of nmax over evaluated particles,
