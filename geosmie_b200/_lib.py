@@ -11,6 +11,7 @@ LIB_PATH = os.environ.get("GEOSMIE_LIB", os.path.join(_HERE, "libgeosmie_b200.so
 GM_NSCAL = 11
 S_W, S_X2W, S_X3W, S_X4W, S_QEXT, S_QSCA, S_QABS, S_QB, S_G, S_CSCA, S_CEXT = range(11)
 F_ELIDE_ZERO_WEIGHT = 1
+PSD_LOGNORM, PSD_SS, PSD_DU, PSD_NPAR = 1, 2, 3, 4
 
 _lib = None
 _lock = threading.Lock()
@@ -37,6 +38,9 @@ SIGNATURES = {
     "gm_table_set_bessel": (C.c_int, [vp, vp, vp, vp]),
     "gm_table_run": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int, vp, vp]),
     "gm_table_run_dev": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int, vp, vp]),
+    "gm_table_set_dr": (C.c_int, [vp, vp]),
+    "gm_table_run_psd": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp]),
+    "gm_table_get_weights": (C.c_int, [vp, C.c_int, C.c_int, vp]),
     "gm_table_device_outputs": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp)]),
     "gm_table_particles": (C.c_int, [vp, C.c_int, vp, vp, vp, vp]),
     "gm_table_last_stats": (C.c_int, [vp, vp]),
@@ -220,6 +224,31 @@ class Table:
         check(self.lib.gm_table_run(self.t, ntask, ptr(mz), ptr(mrel), nmode, ptr(wp), ptr(ws), F_ELIDE_ZERO_WEIGHT if elide else 0,
                                     ptr(scal), ptr(phase)))
         return scal, phase
+
+    def set_dr(self, dr):
+        check(self.lib.gm_table_set_dr(self.t, ptr(f64(dr))))
+
+    def run_psd(self, mz, mrel, kind, params, frac, elide=False):
+        """Weights generated on the device from per-(task, mode) parameters.  params [ntask][nmode][4], frac [ntask][nmode]."""
+        mz = np.ascontiguousarray(np.atleast_1d(mz), dtype=np.complex128)
+        mrel = np.ascontiguousarray(np.atleast_1d(mrel), dtype=np.complex128)
+        ntask = mz.size
+        params = f64(params)
+        nmode = params.shape[1]
+        assert params.shape == (ntask, nmode, PSD_NPAR)
+        frac = f64(np.broadcast_to(frac, (ntask, nmode)))
+        scal = np.empty((ntask, nmode, GM_NSCAL))
+        phase = np.empty((ntask, 4, self.nang))
+        check(self.lib.gm_table_run_psd(self.t, ntask, ptr(mz), ptr(mrel), nmode, int(kind), ptr(params), ptr(frac),
+                                        F_ELIDE_ZERO_WEIGHT if elide else 0, ptr(scal), ptr(phase)))
+        self._last_psd_shape = (ntask, nmode)
+        return scal, phase
+
+    def get_weights(self):
+        ntask, nmode = self._last_psd_shape
+        w = np.empty((ntask, nmode, self.nx))
+        check(self.lib.gm_table_get_weights(self.t, ntask, nmode, ptr(w)))
+        return w
 
     def run_into(self, ntask, mz, mrel, w_phase, scal_out, phase_out, elide=False):
         """Host-buffer call writing into caller-provided (ideally pinned) numpy arrays; single-mode weights."""

@@ -8,6 +8,7 @@
 
 #include "gm_mie_kernels.cuh"
 #include "gm_coated.cuh"
+#include "gm_psd.cuh"
 
 // ------------------------------------------------------------------------------------------------ errors / lifetime
 static thread_local char g_err[512] = "";
@@ -270,7 +271,9 @@ struct gm_table_s {
   DevGroups D;
   std::vector<double> hx;
   std::vector<int32_t> hnmax;
-  DevBuf T, cost;
+  DevBuf T, cost, dr, psd_par, psd_frac;
+  bool have_dr = false;
+  bool psd_separate = false;
   // per-run buffers
   DevBuf coef, gact, scal_part, part, chunk_start, mz, mrel, wphase, wscal, out_scal, out_phase, stats, q, s12;
   double last_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -322,7 +325,7 @@ extern "C" int gm_table_destroy(gm_table_t t) {
   if (!t) return GM_OK;
   cudaSetDevice(t->h->device);
   t->D.release();
-  for (DevBuf* b : {&t->T, &t->cost, &t->coef, &t->gact, &t->scal_part, &t->part, &t->chunk_start, &t->mz, &t->mrel, &t->wphase,
+  for (DevBuf* b : {&t->dr, &t->psd_par, &t->psd_frac, &t->T, &t->cost, &t->coef, &t->gact, &t->scal_part, &t->part, &t->chunk_start, &t->mz, &t->mrel, &t->wphase,
                     &t->wscal, &t->out_scal, &t->out_phase, &t->stats, &t->q, &t->s12})
     b->release();
   for (auto& e : t->evpool) cudaEventDestroy(e);
@@ -618,6 +621,66 @@ extern "C" int gm_table_run(gm_table_t t, int ntask, const double* mz, const dou
                       nullptr, false, &hio);
   if (rc) return rc;
   return fetch_stats(t);
+}
+
+extern "C" int gm_table_set_dr(gm_table_t t, const double* dr) {
+  GM_REQUIRE(t && dr, "NULL argument");
+  GM_CUDA_TRY(cudaSetDevice(t->h->device));
+  int rc = t->dr.ensure(sizeof(double) * t->nx);
+  if (rc) return rc;
+  GM_CUDA_TRY(cudaMemcpyAsync(t->dr.p, dr, sizeof(double) * t->nx, cudaMemcpyHostToDevice, t->h->stream));
+  GM_CUDA_TRY(cudaStreamSynchronize(t->h->stream));
+  t->have_dr = true;
+  return GM_OK;
+}
+
+extern "C" int gm_table_run_psd(gm_table_t t, int ntask, const double* mz, const double* mrel, int nmode, int psd_kind,
+                                const double* psd_params, const double* frac, int flags, double* out_scal, double* out_phase) {
+  GM_REQUIRE(t != nullptr, "table is NULL");
+  GM_REQUIRE(ntask > 0 && nmode >= 1 && nmode <= 32, "ntask / nmode out of range");
+  GM_REQUIRE(mz && mrel && psd_params && frac && out_scal && out_phase, "NULL argument");
+  GM_REQUIRE(psd_kind >= GM_PSD_LOGNORM && psd_kind <= GM_PSD_DU, "unknown psd_kind");
+  GM_REQUIRE(psd_kind != GM_PSD_LOGNORM || t->have_dr, "GM_PSD_LOGNORM needs gm_table_set_dr first");
+  GM_REQUIRE(t->nx >= 2, "need at least two grid points");
+  gm_handle_t h = t->h;
+  GM_CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  int rc;
+  const size_t nw = (size_t)ntask * t->nx;
+  bool separate = nmode > 1;
+  for (int i = 0; i < ntask * nmode && !separate; ++i) separate = frac[i] != 1.0;
+  if ((rc = t->mz.ensure(sizeof(double2) * ntask)) || (rc = t->mrel.ensure(sizeof(double2) * ntask)) ||
+      (rc = t->wphase.ensure(sizeof(double) * nw)) || (rc = t->out_scal.ensure(sizeof(double) * (size_t)ntask * nmode * GM_NSCAL)) ||
+      (rc = t->out_phase.ensure(sizeof(double) * (size_t)ntask * 4 * t->nang)) ||
+      (rc = t->psd_par.ensure(sizeof(double) * (size_t)ntask * nmode * GM_PSD_NPAR)) ||
+      (rc = t->psd_frac.ensure(sizeof(double) * (size_t)ntask * nmode)))
+    return rc;
+  if (separate && (rc = t->wscal.ensure(sizeof(double) * nw * nmode))) return rc;
+  GM_CUDA_TRY(cudaMemcpyAsync(t->mz.p, mz, sizeof(double2) * ntask, cudaMemcpyHostToDevice, st));
+  GM_CUDA_TRY(cudaMemcpyAsync(t->mrel.p, mrel, sizeof(double2) * ntask, cudaMemcpyHostToDevice, st));
+  GM_CUDA_TRY(cudaMemcpyAsync(t->psd_par.p, psd_params, sizeof(double) * (size_t)ntask * nmode * GM_PSD_NPAR, cudaMemcpyHostToDevice, st));
+  GM_CUDA_TRY(cudaMemcpyAsync(t->psd_frac.p, frac, sizeof(double) * (size_t)ntask * nmode, cudaMemcpyHostToDevice, st));
+  k_psd<<<ntask, 256, 0, st>>>(t->nx, nmode, psd_kind, t->D.x.as<double>(), t->dr.as<double>(), t->psd_par.as<double>(),
+                               t->psd_frac.as<double>(), t->wscal.as<double>(), t->wphase.as<double>(), separate ? 1 : 0);
+  GM_LAUNCH_CHECK(h);
+  t->psd_separate = separate;
+  rc = table_run_core(t, ntask, t->mz.as<double>(), t->mrel.as<double>(), nmode, t->wphase.as<double>(),
+                      separate ? t->wscal.as<double>() : nullptr, flags, t->out_scal.as<double>(), t->out_phase.as<double>(), nullptr,
+                      nullptr, false);
+  if (rc) return rc;
+  GM_CUDA_TRY(cudaMemcpyAsync(out_scal, t->out_scal.p, sizeof(double) * (size_t)ntask * nmode * GM_NSCAL, cudaMemcpyDeviceToHost, st));
+  GM_CUDA_TRY(cudaMemcpyAsync(out_phase, t->out_phase.p, sizeof(double) * (size_t)ntask * 4 * t->nang, cudaMemcpyDeviceToHost, st));
+  return fetch_stats(t);
+}
+
+extern "C" int gm_table_get_weights(gm_table_t t, int ntask, int nmode, double* w) {
+  GM_REQUIRE(t && w, "NULL argument");
+  GM_CUDA_TRY(cudaSetDevice(t->h->device));
+  const void* src = t->psd_separate ? t->wscal.p : t->wphase.p;
+  GM_REQUIRE(src != nullptr, "no weights have been generated");
+  GM_CUDA_TRY(cudaMemcpyAsync(w, src, sizeof(double) * (size_t)ntask * nmode * t->nx, cudaMemcpyDeviceToHost, t->h->stream));
+  GM_CUDA_TRY(cudaStreamSynchronize(t->h->stream));
+  return GM_OK;
 }
 
 // device copies of the outputs of the last gm_table_run (host-buffer variant), e.g. to chain gm_gsf_expand_phase4_dev

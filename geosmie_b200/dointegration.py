@@ -395,12 +395,42 @@ def bins_of(params):
     raise ValueError("unknown psd type %r" % t)
 
 
+def psd_parameters(params, radind, onerh, rh, lam):
+    """The per-cell scalars of calculatePSD (dointegration.py:539-664) without its O(nx) array work: what the device
+    kernel k_psd needs to generate the number weights.  Returns (kind, par [nmode][4], rLow, rUp)."""
+    pparam = params['psd']['params']
+    psdtype = params['psd']['type']
+    rparams = params['rhDep']
+    xconv = 2 * np.pi / lam
+    if psdtype == 'lognorm':
+        rmodes = [pp.humidityGrowth(rparams, r0, onerh, rh) for r0 in pparam['r0'][radind]]
+        rmaxs0 = list(pparam['rmax0'][radind])
+        rmaxs = [pp.humidityGrowth(rparams, r, onerh, rh) for r in rmaxs0]
+        rmins = list(pparam['rmin0'][radind])
+        sig = pparam['sigma'][radind]
+        par = [[rmodes[k] * xconv, rmins[k] * xconv, rmaxs[k] * xconv, np.log(sig[k])] for k in range(len(rmodes))]
+        return _lib.PSD_LOGNORM, par, rmins[0], rmaxs0[0]
+    if psdtype == 'ss':
+        rMinMaj, rMaxMaj = pparam['rMinMaj'][radind], pparam['rMaxMaj'][radind]
+        rMinUse = pp.humidityGrowth(rparams, rMinMaj, onerh, rh)
+        rMaxUse = pp.humidityGrowth(rparams, rMaxMaj, onerh, rh)
+        return _lib.PSD_SS, [[xconv, rMinUse, rMaxUse, rMinMaj / rMinUse]], rMinMaj, rMaxMaj
+    if psdtype == 'du':
+        lo, hi = pparam['rMinMaj'][radind], pparam['rMaxMaj'][radind]
+        return _lib.PSD_DU, [[xconv, a, b, 0.0] for a, b in zip(lo, hi)], lo[-1], hi[-1]
+    raise ValueError("unknown psd type %r" % psdtype)
+
+
 class BinPlan(object):
     """Host-side description of one size bin: the grid and, for every (wavelength, RH) cell that must be computed, the
-    refractive indices, number weights and scalars that the reference derives inside its lambda/RH loops
-    (dointegration.py:811-889).  `tasks` flattens the cells into gm_table_run tasks."""
+    refractive indices, the size-distribution inputs and the scalars that the reference derives inside its lambda/RH
+    loops (dointegration.py:811-889).  `tasks` flattens the cells into gm_table_run tasks.
 
-    def __init__(self, params, radind, lambarr, rh_used, part_m, water_m, cells=None):
+    device_psd=True (default in `fun`): only the per-cell PSD parameters are derived here and the weight vectors are
+    generated on the GPU (gm_table_run_psd); device_psd=False builds the weights with numpy exactly like the reference
+    (calculatePSD) and uploads them -- used for validation."""
+
+    def __init__(self, params, radind, lambarr, rh_used, part_m, water_m, cells=None, device_psd=False):
         self.radind = radind
         self.xx, self.dr = initializeXarr(params, radind, lambarr[0], lambarr[-1])
         self.nmax = nmax_of(self.xx)
@@ -409,41 +439,54 @@ class BinPlan(object):
         rhop00 = params['rhop0']
         self.rhop0 = rhop00[radind] if isinstance(rhop00, list) else rhop00
         self.fracs = list(pparam['fracs'][radind])
-        nlam, nrh = len(lambarr), len(rh_used)
         self.nri = len(part_m)
         self.cells = []          # (li, rhi)
         self.trivial = trivial
-        mr_l, w_l, meta = [], [], []
+        self.device_psd = device_psd
+        self.psd_kind = None
+        mr_l, w_l, par_l, meta = [], [], [], []
         want = None if cells is None else set(cells)
+        if device_psd and want is not None:
+            want |= {(li, 0) for (li, _) in want}      # reff_mass0 comes from the RH-index-0 cell of the same wavelength
         for li, lam in enumerate(lambarr):
+            if want is not None and not any(c[0] == li for c in want):
+                continue
             nref0 = [complex(f[0](lam), -f[1](lam)) for f in part_m]      # sign flip of the stored -k (:813-816)
             nrefwater = complex(1, 0) if trivial else complex(water_m[0](lam), water_m[1](lam))
-            _, _, _, rrat0 = getHumidRefractiveIndex(params, radind, 0, rh_used, nref0, nrefwater)
-            _, reff_mass0, _, _ = calculatePSD(params, radind, 0., rh_used, self.xx, self.dr, rrat0, lam)
+            reff_mass0 = None
+            if not device_psd:
+                _, _, _, rrat0 = getHumidRefractiveIndex(params, radind, 0, rh_used, nref0, nrefwater)
+                _, reff_mass0, _, _ = calculatePSD(params, radind, 0., rh_used, self.xx, self.dr, rrat0, lam)
             for rhi, onerh in enumerate(rh_used):
                 if trivial and rhi > 0:
                     continue
                 if want is not None and (li, rhi) not in want:
                     continue
                 mr, mi, gf, rrat = getHumidRefractiveIndex(params, radind, rhi, rh_used, nref0, nrefwater)
-                psd, ref, rLow, rUp = calculatePSD(params, radind, onerh, rh_used, self.xx, self.dr, rrat, lam)
+                if device_psd:
+                    self.psd_kind, par, rLow, rUp = psd_parameters(params, radind, onerh, rh_used, lam)
+                    par_l.append(par)
+                else:
+                    psd, _, rLow, rUp = calculatePSD(params, radind, onerh, rh_used, self.xx, self.dr, rrat, lam)
+                    w_l.append(np.asarray(psd))
                 rhop = rrat ** 3. * self.rhop0 + (1. - rrat ** 3.) * 1000.
                 self.cells.append((li, rhi))
                 mr_l.append([complex(a, b) for a, b in zip(mr, mi)])
-                w_l.append(np.asarray(psd))
-                meta.append((lam, rhop, gf, rLow, rUp, list(reff_mass0)))
-        self.m = np.array(mr_l, dtype=np.complex128).reshape(len(self.cells), self.nri)
-        self.w = np.array(w_l, dtype=float).reshape(len(self.cells), len(self.fracs), self.xx.size)
+                meta.append((lam, rhop, gf, rLow, rUp, None if reff_mass0 is None else list(reff_mass0)))
+        ncell, nmode = len(self.cells), len(self.fracs)
+        self.m = np.array(mr_l, dtype=np.complex128).reshape(ncell, self.nri)
+        self.w = None if device_psd else np.array(w_l, dtype=float).reshape(ncell, nmode, self.xx.size)
+        self.psd_par = np.array(par_l, dtype=float).reshape(ncell, nmode, 4) if device_psd else None
         self.lam = np.array([a[0] for a in meta])
         self.rhop = np.array([a[1] for a in meta])
         self.gf = np.array([a[2] for a in meta])
         self.rLow = np.array([a[3] for a in meta])
         self.rUp = np.array([a[4] for a in meta])
-        self.reff0 = np.array([a[5] for a in meta]).reshape(len(self.cells), len(self.fracs))
+        self.reff0 = None if device_psd else np.array([a[5] for a in meta]).reshape(ncell, nmode)
 
     # ---- flatten to GPU tasks
     def tasks(self):
-        """Returns (mz [ntask], w_phase [ntask][nx], w_scal [ntask][nmode_t][nx], tasks_per_cell)."""
+        """Uploaded-weights path.  Returns (mz [ntask], w_phase [ntask][nx], w_scal [ntask][nmode_t][nx], tasks_per_cell)."""
         fr = np.asarray(self.fracs, dtype=float)
         ncell, nmode, nx = self.w.shape
         if self.nri == 1:
@@ -456,6 +499,28 @@ class BinPlan(object):
         wp = (self.w * fr[None, :, None]).reshape(ncell * nmode, nx)
         return mz, wp, self.w.reshape(ncell * nmode, 1, nx), nmode
 
+    def tasks_psd(self):
+        """Device-PSD path.  Returns (mz [ntask], par [ntask][nmode_t][4], frac [ntask][nmode_t], tasks_per_cell)."""
+        fr = np.asarray(self.fracs, dtype=float)
+        ncell, nmode, _ = self.psd_par.shape
+        if self.nri == 1:
+            return np.sqrt(self.m[:, 0] ** 2 * 1.0), self.psd_par, np.broadcast_to(fr, (ncell, nmode)).copy(), 1
+        assert self.nri == nmode, "one refractive index per PSD mode expected"
+        return (np.sqrt(self.m.reshape(-1) ** 2 * 1.0), self.psd_par.reshape(ncell * nmode, 1, 4),
+                np.tile(fr, ncell).reshape(ncell * nmode, 1), nmode)
+
+    def evaluate(self, table, elide=True):
+        """Run every task of the bin on `table`; returns (scal, phase, tasks_per_cell)."""
+        if self.device_psd:
+            mz, par, fr, tpc = self.tasks_psd()
+            if self.psd_kind == _lib.PSD_LOGNORM:
+                table.set_dr(self.dr)
+            scal, phase = table.run_psd(mz, mz, self.psd_kind, par, fr, elide=elide)
+        else:
+            mz, wp, ws, tpc = self.tasks()
+            scal, phase = table.run(mz, mz, wp, ws, elide=elide)
+        return scal, phase, tpc
+
     def reduce(self, scal, phase, tasks_per_cell):
         """Raw sums of the tasks -> the integratePSD `ret` dict with a leading cell axis."""
         ncell = len(self.cells)
@@ -464,7 +529,13 @@ class BinPlan(object):
         else:
             sc = scal.reshape(ncell, tasks_per_cell, scal.shape[-1])
             ph = phase.reshape(ncell, tasks_per_cell, 4, phase.shape[-1]).sum(axis=1)
-        return combine_modes(sc, ph, self.fracs, self.lam, self.reff0, self.rhop0, self.rhop)
+        reff0 = self.reff0
+        if reff0 is None:
+            # reff_mass0 = sum r^4 w / sum r^3 w of the RH-index-0 weights at the same wavelength (:837-838, :1118-1121)
+            ref = (self.lam / (2. * np.pi))[:, None] * sc[..., _S.S_X4W] / sc[..., _S.S_X3W]
+            dry = {li: i for i, (li, rhi) in enumerate(self.cells) if rhi == 0}
+            reff0 = ref[[dry[li] for li, _ in self.cells]]
+        return combine_modes(sc, ph, self.fracs, self.lam, reff0, self.rhop0, self.rhop)
 
 
 def run_bin(plan, costarr, handle=None, elide=True, table=None):
@@ -472,16 +543,16 @@ def run_bin(plan, costarr, handle=None, elide=True, table=None):
     own = table is None
     if own:
         table = _lib.Table(plan.xx, plan.nmax, costarr, handle)
-    mz, wp, ws, tpc = plan.tasks()
-    scal, phase = table.run(mz, mz, wp, ws, elide=elide)
+    scal, phase, tpc = plan.evaluate(table, elide=elide)
     ret = plan.reduce(scal, phase, tpc)
     return ret, table
 
 
-def fun(partID0, datatype, oppfx, oppclassic, elide=True, write=True, comm=None):
+def fun(partID0, datatype, oppfx, oppclassic, elide=True, write=True, comm=None, device_psd=True):
     """Main table build called from runoptics.py (dointegration.py:672-1036).  Same arguments as the reference plus
-    `elide` (skip exactly-zero-weight particles; result-neutral), `write` (False: return the arrays only) and `comm`
-    (a geosmie_b200.dist.Comm: cells are sharded across ranks and gathered to rank 0).  Returns the dict of arrays
+    `elide` (skip exactly-zero-weight particles; result-neutral), `write` (False: return the arrays only), `comm`
+    (a geosmie_b200.dist.Comm: cells are sharded across ranks and gathered to rank 0) and `device_psd` (True: number
+    weights generated on the GPU from per-cell parameters; False: numpy weights exactly like calculatePSD, uploaded).  Returns the dict of arrays
     written to optics_<id>.nomom[.legacy].nc4 on rank 0 (None elsewhere)."""
     partID = partID0.split('/')[-1].replace(".json", "")
     print("\n ####################\n Starting case %s\n ####################\n" % partID)
@@ -519,18 +590,24 @@ def fun(partID0, datatype, oppfx, oppclassic, elide=True, write=True, comm=None)
         trivial = params['rhDep']['type'] == 'trivial'
         all_cells = [(li, rhi) for li in range(nl) for rhi in range(nr) if not (trivial and rhi > 0)]
         mine = all_cells[rank::world] if world > 1 else None
-        plan = BinPlan(params, radind, lambarr, rh_used, part_m, water_m, cells=mine)
-        mz, wp, ws, tpc = plan.tasks()
+        if mine is not None and device_psd:
+            # keep the RH-index-0 cell of every wavelength on the rank that owns any of its cells (needed for reff_mass0
+            # only after the gather, so sharding stays a plain round-robin): rank r takes wavelengths r, r+W, ...
+            mine = [c for c in all_cells if c[0] % world == rank]
+        plan = BinPlan(params, radind, lambarr, rh_used, part_m, water_m, cells=mine, device_psd=device_psd)
         table = _lib.Table(plan.xx, plan.nmax, costarr)
-        scal, phase = table.run(mz, mz, wp, ws, elide=elide)
+        scal, phase, tpc = plan.evaluate(table, elide=elide)
         table.close()
         if comm is not None and world > 1:
             gathered = comm.gather_cells(scal, phase)
             if rank != 0:
                 continue
             # rank r holds all_cells[r::world]; rebuild the full bin plan metadata on rank 0
-            full = BinPlan(params, radind, lambarr, rh_used, part_m, water_m, cells=None, )
-            order = [c for r in range(world) for c in all_cells[r::world]]
+            full = BinPlan(params, radind, lambarr, rh_used, part_m, water_m, cells=None, device_psd=device_psd)
+            if device_psd:
+                order = [c for r in range(world) for c in all_cells if c[0] % world == r]
+            else:
+                order = [c for r in range(world) for c in all_cells[r::world]]
             pos = {c: i for i, c in enumerate(order)}
             idx = np.array([pos[c] for c in full.cells])
             tsel = (idx[:, None] * tpc + np.arange(tpc)[None, :]).reshape(-1)

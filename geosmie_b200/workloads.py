@@ -50,10 +50,10 @@ def species_inputs(sp, fixture=DEFAULT_FIXTURE):
     return params, ml[0], part_m, water_m, rh_used
 
 
-def bin_plan(sp, radind=0, cells=None, fixture=DEFAULT_FIXTURE):
+def bin_plan(sp, radind=0, cells=None, fixture=DEFAULT_FIXTURE, device_psd=False):
     from . import dointegration as DI
     params, lambarr, part_m, water_m, rh_used = species_inputs(sp, fixture)
-    return DI.BinPlan(params, radind, lambarr, rh_used, part_m, water_m, cells=cells)
+    return DI.BinPlan(params, radind, lambarr, rh_used, part_m, water_m, cells=cells, device_psd=device_psd)
 
 
 def n_bins(sp):

@@ -109,6 +109,25 @@ int gm_table_run(gm_table_t t, int ntask, const double* mz, const double* mrel, 
                  const double* w_scal, int flags, double* out_scal, double* out_phase);
 int gm_table_run_dev(gm_table_t t, int ntask, const double* mz, const double* mrel, int nmode, const double* w_phase,
                      const double* w_scal, int flags, double* out_scal, double* out_phase);
+/*
+ * gm_table_run_psd: like gm_table_run, but the number weights are generated on the device from per-(task, mode)
+ * parameters (replaces the O(nx) numpy work of dointegration.calculatePSD :539-664 / particleparams.getLogNormPSD
+ * :113-127; the scalars below are still derived on the host with the reference's formulas):
+ *   GM_PSD_LOGNORM  params = xmode, xmin, xmax, ln(sigma)   in size-parameter space (r * 2 pi / lambda); needs gm_table_set_dr
+ *   GM_PSD_SS       params = xconv (2 pi / lambda), rMinUse, rMaxUse, rrat     (Gong sea-salt, :585-624)
+ *   GM_PSD_DU       params = xconv, rMinMaj, rMaxMaj, 0                        (r^-4 sub-bins, :626-662)
+ *   psd_params [ntask][nmode][GM_PSD_NPAR], frac [ntask][nmode] (phase weight = sum_mode frac * w_mode)
+ */
+#define GM_PSD_LOGNORM 1
+#define GM_PSD_SS 2
+#define GM_PSD_DU 3
+#define GM_PSD_NPAR 4
+int gm_table_set_dr(gm_table_t t, const double* dr /*[nx] drarr of initializeXarr, dointegration.py:425-463*/);
+int gm_table_run_psd(gm_table_t t, int ntask, const double* mz, const double* mrel, int nmode, int psd_kind,
+                     const double* psd_params, const double* frac, int flags, double* out_scal, double* out_phase);
+/* the generated weights of the last gm_table_run_psd (host copy, for validation): w [ntask][nmode][nx] */
+int gm_table_get_weights(gm_table_t t, int ntask, int nmode, double* w);
+
 /* device copies of the outputs of the last host-buffer gm_table_run (valid until the next call on this table), so that
  * gm_gsf_expand_phase4_dev can be chained without a host round trip */
 int gm_table_device_outputs(gm_table_t t, double** out_scal, double** out_phase);

@@ -55,3 +55,18 @@ def fun_fixture(name):
     files = dict(json.loads(str(g["files_json"])))
     files[base + ".json"] = str(g["config_json"])
     return g, files, base
+
+
+def species_files(sp):
+    """Files for a run dir that reproduce a shipped species config (su / ss / bc) from the recorded fixture: <sp>.json with
+    the parameters of src/config/geosparticles/<sp>.json and its refractive-index table re-written in 'wsv' format."""
+    from geosmie_b200.workloads import SPECIES
+    ml = load("hostlogic.npz")[sp + "__mlist"]
+    lines = []
+    for i in range(ml.shape[1]):
+        um = float("%.10g" % (ml[0, i] * 1e6))
+        assert um * 1e-6 == ml[0, i]
+        lines.append("%.17g %.17g %.17g" % (um, ml[1, i], ml[2, i]))
+    cfg = json.loads(json.dumps(SPECIES[sp]))
+    cfg["ri"] = {"format": "wsv", "path": ["ri-%s.wsv" % sp]}
+    return {sp + ".json": json.dumps(cfg), "ri-%s.wsv" % sp: "\n".join(lines) + "\n"}

@@ -27,12 +27,11 @@ def build(sp, dense):
     rets = []
     for b in range(workloads.n_bins(sp)):
         t0 = time.time()
-        plan = workloads.bin_plan(sp, b)
-        mz, wp, ws, tpc = plan.tasks()
+        plan = workloads.bin_plan(sp, b, device_psd=DEVICE_PSD)
         t1 = time.time()
         table = _lib.Table(plan.xx, plan.nmax, cost, h)
         table.set_timing(True)
-        scal, phase = table.run(mz, mz, wp, ws, elide=not dense)
+        scal, phase, tpc = plan.evaluate(table, elide=not dense)
         t2 = time.time()
         k = table.last_kernel_ms()
         st = table.last_stats()
@@ -51,10 +50,12 @@ def build(sp, dense):
         t_gsf += t4 - t3
         evals += len(plan.cells) * plan.xx.size
         rets.append((ret, coef))
-    return {"species": sp, "dense": dense, "grid_particle_evals": evals, "host_inputs_s": t_host, "gpu_call_s": t_gpu, "gsf_s": t_gsf,
+    return {"species": sp, "dense": dense, "device_psd": DEVICE_PSD, "grid_particle_evals": evals, "host_inputs_s": t_host, "gpu_call_s": t_gpu, "gsf_s": t_gsf,
             "total_s": t_host + t_gpu + t_gsf, "kernel_ms": kms, "stats": stats_tot,
             "grid_evals_per_s_gpu_call": evals / t_gpu}
 
+
+DEVICE_PSD = "--host-psd" not in sys.argv
 
 if __name__ == "__main__":
     args = [a for a in sys.argv[1:] if not a.startswith("--")] or ["su", "bc", "ss"]
