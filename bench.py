@@ -10,7 +10,9 @@ Refractive indices are the OPAC sulfate / HITRAN water values recorded in tests/
 
 One "step" = one pass of the hot path over that batch:
   value  particle-evals/s with inputs (m, weights) resident in HBM (device-pointer C ABI, CUDA-event timed);
-  e2e    the same through the host-buffer C ABI (pinned host inputs -> H2D -> kernels -> D2H inside the timed region);
+  e2e    the same through the host-buffer C ABI the table driver uses (gm_table_run_psd: per-cell refractive indices and
+         size-distribution parameters in pinned host memory -> H2D -> kernels -> D2H of the reduced sums and GSF moments
+         into pinned host memory, all inside the timed region);
   roofline   FP64 tensor (DMMA) roofline of the dominant kernel k_contract, duration from CUDA events recorded around
              each of its launches on the launching stream inside the timed steps;
   cpu_baseline   the CPU oracle port (oracle/mie_oracle.c, OpenMP) on a bounded sample of the same cells.
@@ -164,7 +166,7 @@ def main():
         return run_reference(args)
 
     import torch
-    from geosmie_b200 import _lib
+    from geosmie_b200 import _lib, workloads
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -211,13 +213,19 @@ def main():
             torch.cat([scal_d.reshape(ncell, -1), phase_d.reshape(ncell, -1), coef_d.reshape(ncell, -1)], dim=1, out=packed)
             td.gather(packed, gather_buf, dst=0)
 
+    # the public call of the table build (dointegration.fun -> BinPlan.evaluate -> gm_table_run_psd): per-cell refractive
+    # index and PSD parameters in, reduced sums out; the number weights are generated on the device
+    plan_psd = workloads.bin_plan("su", 0, device_psd=True)
+    mz_psd, psd_par, psd_frac, _ = plan_psd.tasks_psd()
+    psd_kind = plan_psd.psd_kind
+    table.set_dr(plan_psd.dr)
     mz_hn, w_hn = mz_h.numpy(), w_h.numpy()          # views of the pinned host buffers
     scal_hn, phase_hn = scal_h.numpy(), phase_h.numpy()
 
     def step_e2e():
         # the user-facing call with HOST buffers (gm_table_run): H2D of this step's inputs, kernels and D2H of the results,
         # pipelined batch by batch inside the library; then the GSF expansion of the device copy and D2H of the moments
-        table.run_into(ncell, mz_hn, mz_hn, w_hn, scal_hn, phase_hn, elide=False)
+        table.run_psd(mz_psd, mz_psd, psd_kind, psd_par, psd_frac, elide=False, out=(scal_hn, phase_hn))
         _, ph_ptr = table.device_outputs()
         h.gsf_expand_phase4_dev(ang, ncell, ph_ptr, coef_d.data_ptr(), cn_d.data_ptr())
         coef_h.copy_(coef_d, non_blocking=True)
@@ -276,7 +284,8 @@ def main():
                    "l2_policy": "inputs larger than L2 per step: 78 MB weights + 2.9 GB coefficient stream re-written every step",
                    "parallelism": "cells sharded, %d rank(s), NCCL gather to rank 0" % world},
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": int(mz_h.numel() * 8 + w_h.numel() * 8),
+                "h2d_bytes_per_step": int(mz_psd.nbytes * 2 + psd_par.nbytes + psd_frac.nbytes),
+                "api": "gm_table_run_psd (host buffers: per-cell m and PSD parameters in, reduced sums out) + gm_gsf_expand_phase4_dev",
                 "d2h_bytes_per_step": int(scal_h.numel() * 8 + phase_h.numel() * 8 + coef_h.numel() * 8)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "k_contract<false> (FP64 DMMA m8n8k4)", "achieved": ach, "peak": FP64_PEAK_TFLOPS,

@@ -228,8 +228,9 @@ class Table:
     def set_dr(self, dr):
         check(self.lib.gm_table_set_dr(self.t, ptr(f64(dr))))
 
-    def run_psd(self, mz, mrel, kind, params, frac, elide=False):
-        """Weights generated on the device from per-(task, mode) parameters.  params [ntask][nmode][4], frac [ntask][nmode]."""
+    def run_psd(self, mz, mrel, kind, params, frac, elide=False, out=None):
+        """Weights generated on the device from per-(task, mode) parameters.  params [ntask][nmode][4], frac [ntask][nmode].
+        `out` = (scal, phase) caller-provided (e.g. pinned) arrays."""
         mz = np.ascontiguousarray(np.atleast_1d(mz), dtype=np.complex128)
         mrel = np.ascontiguousarray(np.atleast_1d(mrel), dtype=np.complex128)
         ntask = mz.size
@@ -237,8 +238,7 @@ class Table:
         nmode = params.shape[1]
         assert params.shape == (ntask, nmode, PSD_NPAR)
         frac = f64(np.broadcast_to(frac, (ntask, nmode)))
-        scal = np.empty((ntask, nmode, GM_NSCAL))
-        phase = np.empty((ntask, 4, self.nang))
+        scal, phase = out if out is not None else (np.empty((ntask, nmode, GM_NSCAL)), np.empty((ntask, 4, self.nang)))
         check(self.lib.gm_table_run_psd(self.t, ntask, ptr(mz), ptr(mrel), nmode, int(kind), ptr(params), ptr(frac),
                                         F_ELIDE_ZERO_WEIGHT if elide else 0, ptr(scal), ptr(phase)))
         self._last_psd_shape = (ntask, nmode)

@@ -488,8 +488,9 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
     GM_CUDA_TRY(cudaStreamWaitEvent(t->d2h_stream, t->io_events[2 * nbatch], 0));
     for (int b = 0; b < nbatch; ++b) {
       const int t0 = b * tb, nt = std::min(tb, ntask - t0);
-      GM_CUDA_TRY(cudaMemcpyAsync(const_cast<double*>(d_wphase) + (size_t)t0 * G.nx, hio->w_phase + (size_t)t0 * G.nx,
-                                  sizeof(double) * (size_t)nt * G.nx, cudaMemcpyHostToDevice, t->h2d_stream));
+      if (hio->w_phase)
+        GM_CUDA_TRY(cudaMemcpyAsync(const_cast<double*>(d_wphase) + (size_t)t0 * G.nx, hio->w_phase + (size_t)t0 * G.nx,
+                                    sizeof(double) * (size_t)nt * G.nx, cudaMemcpyHostToDevice, t->h2d_stream));
       if (hio->w_scal)
         GM_CUDA_TRY(cudaMemcpyAsync(const_cast<double*>(d_wscal) + (size_t)t0 * nmode * G.nx, hio->w_scal + (size_t)t0 * nmode * G.nx,
                                     sizeof(double) * (size_t)nt * nmode * G.nx, cudaMemcpyHostToDevice, t->h2d_stream));
@@ -664,12 +665,11 @@ extern "C" int gm_table_run_psd(gm_table_t t, int ntask, const double* mz, const
                                t->psd_frac.as<double>(), t->wscal.as<double>(), t->wphase.as<double>(), separate ? 1 : 0);
   GM_LAUNCH_CHECK(h);
   t->psd_separate = separate;
+  HostIO hio = {nullptr, nullptr, out_scal, out_phase};   // results are downloaded batch by batch behind the kernels
   rc = table_run_core(t, ntask, t->mz.as<double>(), t->mrel.as<double>(), nmode, t->wphase.as<double>(),
                       separate ? t->wscal.as<double>() : nullptr, flags, t->out_scal.as<double>(), t->out_phase.as<double>(), nullptr,
-                      nullptr, false);
+                      nullptr, false, &hio);
   if (rc) return rc;
-  GM_CUDA_TRY(cudaMemcpyAsync(out_scal, t->out_scal.p, sizeof(double) * (size_t)ntask * nmode * GM_NSCAL, cudaMemcpyDeviceToHost, st));
-  GM_CUDA_TRY(cudaMemcpyAsync(out_phase, t->out_phase.p, sizeof(double) * (size_t)ntask * 4 * t->nang, cudaMemcpyDeviceToHost, st));
   return fetch_stats(t);
 }
 
