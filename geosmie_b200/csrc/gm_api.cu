@@ -551,9 +551,9 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
     C.s12 = d_s12 ? d_s12 + (size_t)t0 * G.nx * t->nang * 4 : nullptr;
     if ((rc = ev_mark(t, 1))) return rc;
     if (per_particle)
-      k_contract<true><<<nt * 2 * nchunk, GM_CONTRACT_WARPS * 32, smem, st>>>(C);
+      k_contract<true><<<nt * 2 * nchunk, GM_CONTRACT_THREADS, smem, st>>>(C);
     else
-      k_contract<false><<<nt * 2 * nchunk, GM_CONTRACT_WARPS * 32, smem, st>>>(C);
+      k_contract<false><<<nt * 2 * nchunk, GM_CONTRACT_THREADS, smem, st>>>(C);
     GM_LAUNCH_CHECK(h);
     if ((rc = ev_mark(t, 1))) return rc;
     if (!per_particle) {

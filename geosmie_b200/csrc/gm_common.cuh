@@ -81,29 +81,17 @@ constexpr int GM_TROW = 2 * GM_LAH;   // p_n row then q_n row
 constexpr int GM_SB = 132;            // doubles per coefficient row: 64 (c+) + 64 (c-) + 4 pad (stride 4 mod 16 -> conflict-free B fragments)
 constexpr int GM_KSTEP = 4;           // DMMA k extent
 constexpr int GM_STAGE_DBL = GM_KSTEP * GM_TROW + GM_KSTEP * GM_SB;
-#ifndef GM_X_NOEMPTY
-#define GM_X_NOEMPTY 0
-#endif
-#ifndef GM_X_NOFULL
-#define GM_X_NOFULL 0
-#endif
-#ifndef GM_EARLY_TEST
-#define GM_EARLY_TEST 0
+#ifndef GM_PRODUCER_WARP
+#define GM_PRODUCER_WARP 1   // 1: dedicated TMA producer warp (4th warpgroup, setmaxnreg); 0: thread 0 of warp 0 produces
 #endif
 #ifndef GM_WANT_ITEMS_CFG
 #define GM_WANT_ITEMS_CFG 32
 #endif
-#ifndef GM_SPS_CFG
-#define GM_SPS_CFG 1
-#endif
-#ifndef GM_STAGES_CFG
-#define GM_STAGES_CFG 8
-#endif
-constexpr int GM_SPS = GM_SPS_CFG;        // k4 steps per pipeline stage (one mbarrier round trip per stage)
-constexpr int GM_STAGES = GM_STAGES_CFG;  // pipeline stages
-constexpr int GM_CONTRACT_WARPS = 12;
+constexpr int GM_STAGES = 8;              // pipeline stages (one k4 step each)
+constexpr int GM_CONTRACT_WARPS = 12;     // consumer (MMA) warps
+constexpr int GM_CONTRACT_THREADS = (GM_CONTRACT_WARPS + (GM_PRODUCER_WARP ? 4 : 0)) * 32;
 constexpr int GM_MAX_CHUNK_GROUPS = 1024;   // group metadata staged in shared memory per contraction CTA
-constexpr int GM_CONTRACT_SMEM = GM_STAGES * GM_SPS * GM_STAGE_DBL * 8 + 2 * GM_STAGES * 8 + GM_MAX_CHUNK_GROUPS * 8;
+constexpr int GM_CONTRACT_SMEM = GM_STAGES * GM_STAGE_DBL * 8 + 2 * GM_STAGES * 8 + GM_MAX_CHUNK_GROUPS * 8;
 
 // ------------------------------------------------------------------------------------------------ complex helpers
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {

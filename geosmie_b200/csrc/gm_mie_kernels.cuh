@@ -423,10 +423,10 @@ struct ContractArgs {
 // GM_STAGES-deep shared-memory ring by 1-D bulk copies (TMA) signalled through mbarriers.  The C fragment gives each
 // lane (Re, Im) of S+ and S- of particle 4j + lane%4 at angle 8i + lane/4, so the Mueller products are lane-local.
 template <bool PER_PARTICLE>
-__global__ void __launch_bounds__(GM_CONTRACT_WARPS * 32, 1) k_contract(ContractArgs A) {
+__global__ void __launch_bounds__(GM_CONTRACT_THREADS, 1) k_contract(ContractArgs A) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* stages = reinterpret_cast<double*>(smem_raw);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)GM_STAGES * GM_SPS * GM_STAGE_DBL * 8);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)GM_STAGES * GM_STAGE_DBL * 8);
   uint64_t* empty = full + GM_STAGES;
   int2* meta = reinterpret_cast<int2*>(empty + GM_STAGES);   // per group of the chunk: (k4 steps or 0 if inactive, first row)
 
@@ -453,28 +453,22 @@ __global__ void __launch_bounds__(GM_CONTRACT_WARPS * 32, 1) k_contract(Contract
   __syncthreads();
   int nsteps = 0;
   for (int g = 0; g < ng; ++g) nsteps += meta[g].x;
-
-  const double* Th = A.T + (size_t)half * A.nrows * GM_TROW;
-  const double* coef_t = A.coef + (size_t)task * A.task_stride;
-
-  // producer cursor (thread 0 only): next (group, k) to fetch.  A stage holds GM_SPS consecutive k4 steps and has one
-  // full / one empty mbarrier, so the consumers pay one barrier round trip per GM_SPS steps.
-  int pg = 0, pk = 0, pstage = 0;
-  while (pg < ng && meta[pg].x == 0) ++pg;
-  const int nstages = (nsteps + GM_SPS - 1) / GM_SPS;
   constexpr uint32_t TBYTES = GM_KSTEP * GM_TROW * 8, CBYTES = GM_KSTEP * GM_SB * 8;
-  // fetch as many stages as are free, never blocking: a stage is free once all 12 warps released its previous use
-  // (non-blocking mbarrier test), so the producer never stalls warp 0's own MMA stream
-  auto produce = [&](int consumed_stage) {
-    while (pstage < nstages && pstage < consumed_stage + GM_STAGES) {
-      const int s = pstage % GM_STAGES;
-#if !GM_X_NOEMPTY
-      if (pstage >= GM_STAGES && !mbar_test(&empty[s], ((pstage / GM_STAGES) - 1) & 1)) break;
-#endif
-      const int nsub = min(GM_SPS, nsteps - pstage * GM_SPS);
-      mbar_expect_tx(&full[s], (uint32_t)nsub * (TBYTES + CBYTES));
-      for (int u = 0; u < nsub; ++u) {
-        double* dst = stages + ((size_t)s * GM_SPS + u) * GM_STAGE_DBL;
+
+#if GM_PRODUCER_WARP
+  // ---- warp specialisation: the 4th warpgroup gives its registers back and one of its threads becomes the TMA producer
+  if (warp >= GM_CONTRACT_WARPS) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    if (warp == GM_CONTRACT_WARPS && lane == 0) {
+      const double* Th = A.T + (size_t)half * A.nrows * GM_TROW;
+      const double* coef_t = A.coef + (size_t)task * A.task_stride;
+      int pg = 0, pk = 0;
+      while (pg < ng && meta[pg].x == 0) ++pg;
+      for (int pstep = 0; pstep < nsteps; ++pstep) {
+        const int s = pstep % GM_STAGES;
+        if (pstep >= GM_STAGES) mbar_wait(&empty[s], ((pstep / GM_STAGES) - 1) & 1);   // all 12 consumer warps released it
+        double* dst = stages + (size_t)s * GM_STAGE_DBL;
+        mbar_expect_tx(&full[s], TBYTES + CBYTES);
         bulk_g2s(dst, Th + (size_t)pk * GM_KSTEP * GM_TROW, TBYTES, &full[s]);
         bulk_g2s(dst + GM_KSTEP * GM_TROW, coef_t + ((size_t)meta[pg].y + (size_t)pk * GM_KSTEP) * GM_SB, CBYTES, &full[s]);
         if (++pk == meta[pg].x) {
@@ -483,10 +477,35 @@ __global__ void __launch_bounds__(GM_CONTRACT_WARPS * 32, 1) k_contract(Contract
           while (pg < ng && meta[pg].x == 0) ++pg;
         }
       }
-      ++pstage;
+    }
+    return;
+  }
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
+#else
+  const double* Th = A.T + (size_t)half * A.nrows * GM_TROW;
+  const double* coef_t = A.coef + (size_t)task * A.task_stride;
+  // producer = thread 0 of warp 0: fetches as many steps as there are free stages, never blocking (a stage is free once
+  // all 12 warps released its previous use: non-blocking mbarrier test)
+  int pg = 0, pk = 0, pstep = 0;
+  while (pg < ng && meta[pg].x == 0) ++pg;
+  auto produce = [&](int consumed) {
+    while (pstep < nsteps && pstep < consumed + GM_STAGES) {
+      const int s = pstep % GM_STAGES;
+      if (pstep >= GM_STAGES && !mbar_test(&empty[s], ((pstep / GM_STAGES) - 1) & 1)) break;
+      double* dst = stages + (size_t)s * GM_STAGE_DBL;
+      mbar_expect_tx(&full[s], TBYTES + CBYTES);
+      bulk_g2s(dst, Th + (size_t)pk * GM_KSTEP * GM_TROW, TBYTES, &full[s]);
+      bulk_g2s(dst + GM_KSTEP * GM_TROW, coef_t + ((size_t)meta[pg].y + (size_t)pk * GM_KSTEP) * GM_SB, CBYTES, &full[s]);
+      ++pstep;
+      if (++pk == meta[pg].x) {
+        pk = 0;
+        ++pg;
+        while (pg < ng && meta[pg].x == 0) ++pg;
+      }
     }
   };
   if (threadIdx.x == 0) produce(0);
+#endif
 
   double accp[2][8][2], accm[2][8][2];
 #pragma unroll
@@ -499,24 +518,17 @@ __global__ void __launch_bounds__(GM_CONTRACT_WARPS * 32, 1) k_contract(Contract
 
   const int a0 = warp * 16;
   int step = 0;
-#if GM_EARLY_TEST
-  bool ready = false;   // full barrier of the current step already observed complete (tested one step early)
-#endif
   for (int gi = 0; gi < ng; ++gi) {
     const int nk = meta[gi].x;
     if (nk == 0) continue;
     const int g = cs + gi;
     for (int k = 0; k < nk; ++k, ++step) {
       const int s = step % GM_STAGES;
-#if GM_EARLY_TEST
-      if (!ready) mbar_wait(&full[s], (step / GM_STAGES) & 1);
-#else
+#if !GM_PRODUCER_WARP
       if (threadIdx.x == 0) produce(step);
       __syncwarp();
-#if !GM_X_NOFULL
+#endif
       mbar_wait(&full[s], (step / GM_STAGES) & 1);
-#endif
-#endif
       const double* tb = stages + (size_t)s * GM_STAGE_DBL + lk * GM_TROW + a0 + lr;
       const double* cf = stages + (size_t)s * GM_STAGE_DBL + GM_KSTEP * GM_TROW + lk * GM_SB + lr;
       double ap[2], aq[2];
@@ -525,11 +537,6 @@ __global__ void __launch_bounds__(GM_CONTRACT_WARPS * 32, 1) k_contract(Contract
         ap[i] = tb[8 * i];
         aq[i] = tb[GM_LAH + 8 * i];
       }
-#if GM_EARLY_TEST
-      // next step's full barrier is tested here (non-blocking); the result is only consumed after the 32 DMMAs
-      const int nx_s = (step + 1) % GM_STAGES;
-      const bool ok = (step + 1 < nsteps) && mbar_test(&full[nx_s], ((step + 1) / GM_STAGES) & 1);
-#endif
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const double bp = cf[8 * j];
@@ -540,14 +547,8 @@ __global__ void __launch_bounds__(GM_CONTRACT_WARPS * 32, 1) k_contract(Contract
           dmma884(accm[i][j][0], accm[i][j][1], aq[i], bm);
         }
       }
-#if !GM_X_NOEMPTY
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
-#endif
-#if GM_EARLY_TEST
-      if (threadIdx.x == 0) produce(step + 1);
-      ready = __all_sync(0xffffffffu, ok);
-#endif
     }
     // group epilogue
 #pragma unroll
