@@ -38,6 +38,7 @@ SIGNATURES = {
     "gm_table_set_bessel": (C.c_int, [vp, vp, vp, vp]),
     "gm_table_run": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int, vp, vp]),
     "gm_table_run_dev": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int, vp, vp]),
+    "gm_table_run_coated": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, C.c_int, vp, vp]),
     "gm_table_set_dr": (C.c_int, [vp, vp]),
     "gm_table_run_psd": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp]),
     "gm_table_get_weights": (C.c_int, [vp, C.c_int, C.c_int, vp]),
@@ -223,6 +224,23 @@ class Table:
         phase = np.empty((ntask, 4, self.nang))
         check(self.lib.gm_table_run(self.t, ntask, ptr(mz), ptr(mrel), nmode, ptr(wp), ptr(ws), F_ELIDE_ZERO_WEIGHT if elide else 0,
                                     ptr(scal), ptr(phase)))
+        return scal, phase
+
+    def run_coated(self, m1, m2, core_ratio, w_phase, w_scal=None, elide=False):
+        """Coated spheres on the table's grid (= shell size parameter).  m1/m2 [ntask] complex indices, core_ratio [ntask]."""
+        m1 = np.ascontiguousarray(np.atleast_1d(m1), dtype=np.complex128)
+        m2 = np.ascontiguousarray(np.atleast_1d(m2), dtype=np.complex128)
+        ntask = m1.size
+        ratio = f64(np.broadcast_to(core_ratio, (ntask,)))
+        wp = f64(w_phase).reshape(ntask, self.nx)
+        nmode, ws = 1, None
+        if w_scal is not None:
+            ws = f64(w_scal)
+            nmode = ws.shape[1]
+        scal = np.empty((ntask, nmode, GM_NSCAL))
+        phase = np.empty((ntask, 4, self.nang))
+        check(self.lib.gm_table_run_coated(self.t, ntask, ptr(m1), ptr(m2), ptr(ratio), nmode, ptr(wp), ptr(ws),
+                                           F_ELIDE_ZERO_WEIGHT if elide else 0, ptr(scal), ptr(phase)))
         return scal, phase
 
     def set_dr(self, dr):

@@ -185,12 +185,12 @@ extern "C" int gm_mie_eval(gm_handle_t h, int n, const double* x, const double* 
     // per-particle scratch: 3 D arrays + psi/chi at v, w (complex) and y (real)
     std::vector<long long> soff(n + 1, 0);
     for (int i = 0; i < n; ++i) soff[i + 1] = soff[i] + (long long)(nmax[i] + 1);
-    if ((rc = W[3].ensure(sizeof(double) * 16 * soff[n]))) return rc;
+    if ((rc = W[3].ensure(sizeof(double) * 8 * soff[n]))) return rc;
     if ((rc = W[2].ensure(sizeof(long long) * (n + 1)))) return rc;
     GM_CUDA_TRY(cudaMemcpyAsync(W[2].p, soff.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, st));
     k_coated_coeff<<<(n + 63) / 64, 64, 0, st>>>(n, W[15].as<double>(), W[0].as<double>(), W[5].as<double2>(), W[6].as<double2>(),
                                                   mat_stride, W[1].as<int>(), W[2].as<long long>(), W[3].as<double>(),
-                                                  W[7].as<long long>(), W[8].as<double4>());
+                                                  W[7].as<long long>(), W[8].as<double4>(), nullptr, 0, 0);
     GM_LAUNCH_CHECK(h);
     k_props_nat<<<(n + 127) / 128, 128, 0, st>>>(n, W[0].as<double>(), W[1].as<int>(), W[7].as<long long>(), W[8].as<double4>(),
                                                  W[9].as<double>());
@@ -272,6 +272,8 @@ struct gm_table_s {
   std::vector<double> hx;
   std::vector<int32_t> hnmax;
   DevBuf T, cost, dr, psd_par, psd_frac;
+  DevBuf c_ab, c_scratch, c_soff, c_aboff, c_ratio;   // coated-sphere table path
+  long long c_nab = 0, c_nscr = 0;
   bool have_dr = false;
   bool psd_separate = false;
   // per-run buffers
@@ -325,7 +327,7 @@ extern "C" int gm_table_destroy(gm_table_t t) {
   if (!t) return GM_OK;
   cudaSetDevice(t->h->device);
   t->D.release();
-  for (DevBuf* b : {&t->dr, &t->psd_par, &t->psd_frac, &t->T, &t->cost, &t->coef, &t->gact, &t->scal_part, &t->part, &t->chunk_start, &t->mz, &t->mrel, &t->wphase,
+  for (DevBuf* b : {&t->c_ab, &t->c_scratch, &t->c_soff, &t->c_aboff, &t->c_ratio, &t->dr, &t->psd_par, &t->psd_frac, &t->T, &t->cost, &t->coef, &t->gact, &t->scal_part, &t->part, &t->chunk_start, &t->mz, &t->mrel, &t->wphase,
                     &t->wscal, &t->out_scal, &t->out_phase, &t->stats, &t->q, &t->s12})
     b->release();
   for (auto& e : t->evpool) cudaEventDestroy(e);
@@ -430,7 +432,7 @@ struct HostIO {
 // are downloaded while batch b+1 computes.
 static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const double* d_mrel, int nmode, const double* d_wphase,
                           const double* d_wscal, int flags, double* d_out_scal, double* d_out_phase, double* d_q, double* d_s12,
-                          bool per_particle, const HostIO* hio = nullptr) {
+                          bool per_particle, const HostIO* hio = nullptr, const double* d_core_ratio = nullptr) {
   gm_handle_t h = t->h;
   cudaStream_t st = h->stream;
   const Groups& G = t->G;
@@ -440,6 +442,13 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
   int tb = (int)std::max<size_t>(1, h->coef_budget_bytes / std::max<size_t>(per_task_bytes, 1));
   tb = std::min(tb, ntask);
   tb = std::min(tb, 32768);  // grid.y limit of k_coeff
+  if (d_core_ratio) {
+    // coated spheres: natural-layout a_n, b_n + recurrence scratch per (task, particle) are staged in HBM
+    const size_t per_task = (size_t)t->c_nab * sizeof(double4) + (size_t)t->c_nscr * 8 * sizeof(double);
+    tb = std::min(tb, (int)std::max<size_t>(1, ((size_t)1 << 30) / std::max<size_t>(per_task, 1)));
+    if ((rc = t->c_ab.ensure((size_t)tb * t->c_nab * sizeof(double4))) || (rc = t->c_scratch.ensure((size_t)tb * t->c_nscr * 8 * sizeof(double))))
+      return rc;
+  }
   if (hio && ntask >= 256) tb = std::min(tb, (ntask + 3) / 4);   // at least 4 batches so that copies overlap compute
   // chunks: enough CTAs to fill the machine ~8x over, cost-balanced by k4 steps
   const int want_items = GM_WANT_ITEMS_CFG * h->sm_count;   // equal-cost CTAs per SM: bounds the last-wave tail
@@ -528,7 +537,20 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
     A.q = d_q ? d_q + (size_t)t0 * G.nx * 6 : nullptr;
     A.stats = t->stats.as<unsigned long long>();
     if ((rc = ev_mark(t, 0))) return rc;
-    k_coeff<0><<<dim3((G.ngroup + 3) / 4, nt), 128, 0, st>>>(A);
+    if (d_core_ratio) {
+      // mz carries the core index m1 = sqrt(eps1), mrel the shell index m2 = sqrt(eps2) (gm_mie_eval convention)
+      k_coated_coeff<<<dim3((G.nx + 63) / 64, nt), 64, 0, st>>>(G.nx, nullptr, t->D.x.as<double>(), A.mz, A.mrel, 2, t->D.nmax.as<int>(),
+                                                                 t->c_soff.as<long long>(), t->c_scratch.as<double>(),
+                                                                 t->c_aboff.as<long long>(), t->c_ab.as<double4>(), d_core_ratio + t0,
+                                                                 t->c_nscr * 8, t->c_nab);
+      GM_LAUNCH_CHECK(h);
+      A.aboff = t->c_aboff.as<long long>();
+      A.ab = t->c_ab.as<double4>();
+      A.ab_stride = t->c_nab;
+      k_coeff<2><<<dim3((G.ngroup + 3) / 4, nt), 128, 0, st>>>(A);
+    } else {
+      k_coeff<0><<<dim3((G.ngroup + 3) / 4, nt), 128, 0, st>>>(A);
+    }
     GM_LAUNCH_CHECK(h);
     if ((rc = ev_mark(t, 0))) return rc;
 
@@ -620,6 +642,48 @@ extern "C" int gm_table_run(gm_table_t t, int ntask, const double* mz, const dou
   rc = table_run_core(t, ntask, t->mz.as<double>(), t->mrel.as<double>(), nmode, t->wphase.as<double>(),
                       w_scal ? t->wscal.as<double>() : nullptr, flags, t->out_scal.as<double>(), t->out_phase.as<double>(), nullptr,
                       nullptr, false, &hio);
+  if (rc) return rc;
+  return fetch_stats(t);
+}
+
+extern "C" int gm_table_run_coated(gm_table_t t, int ntask, const double* m1, const double* m2, const double* core_ratio, int nmode,
+                                   const double* w_phase, const double* w_scal, int flags, double* out_scal, double* out_phase) {
+  GM_REQUIRE(t != nullptr, "table is NULL");
+  GM_REQUIRE(ntask > 0 && nmode >= 1 && nmode <= 32, "ntask / nmode out of range");
+  GM_REQUIRE(m1 && m2 && core_ratio && w_phase && out_scal && out_phase, "NULL argument");
+  GM_REQUIRE(w_scal || nmode == 1, "w_scal is required when nmode > 1");
+  for (int i = 0; i < ntask; ++i) GM_REQUIRE(core_ratio[i] > 0.0 && core_ratio[i] < 1.0, "core_ratio must be in (0, 1)");
+  gm_handle_t h = t->h;
+  GM_CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  int rc;
+  if (!t->c_soff.p) {
+    std::vector<long long> soff(t->nx + 1, 0), aboff(t->nx + 1, 0);
+    for (int i = 0; i < t->nx; ++i) {
+      soff[i + 1] = soff[i] + t->hnmax[i] + 1;
+      aboff[i + 1] = aboff[i] + t->hnmax[i];
+    }
+    t->c_nscr = soff[t->nx];
+    t->c_nab = aboff[t->nx];
+    if ((rc = t->c_soff.ensure(sizeof(long long) * (t->nx + 1))) || (rc = t->c_aboff.ensure(sizeof(long long) * (t->nx + 1)))) return rc;
+    GM_CUDA_TRY(cudaMemcpyAsync(t->c_soff.p, soff.data(), sizeof(long long) * (t->nx + 1), cudaMemcpyHostToDevice, st));
+    GM_CUDA_TRY(cudaMemcpyAsync(t->c_aboff.p, aboff.data(), sizeof(long long) * (t->nx + 1), cudaMemcpyHostToDevice, st));
+    GM_CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  const size_t nw = (size_t)ntask * t->nx;
+  if ((rc = t->mz.ensure(sizeof(double2) * ntask)) || (rc = t->mrel.ensure(sizeof(double2) * ntask)) ||
+      (rc = t->c_ratio.ensure(sizeof(double) * ntask)) || (rc = t->wphase.ensure(sizeof(double) * nw)) ||
+      (rc = t->out_scal.ensure(sizeof(double) * (size_t)ntask * nmode * GM_NSCAL)) ||
+      (rc = t->out_phase.ensure(sizeof(double) * (size_t)ntask * 4 * t->nang)))
+    return rc;
+  if (w_scal && (rc = t->wscal.ensure(sizeof(double) * nw * nmode))) return rc;
+  GM_CUDA_TRY(cudaMemcpyAsync(t->mz.p, m1, sizeof(double2) * ntask, cudaMemcpyHostToDevice, st));
+  GM_CUDA_TRY(cudaMemcpyAsync(t->mrel.p, m2, sizeof(double2) * ntask, cudaMemcpyHostToDevice, st));
+  GM_CUDA_TRY(cudaMemcpyAsync(t->c_ratio.p, core_ratio, sizeof(double) * ntask, cudaMemcpyHostToDevice, st));
+  HostIO hio = {w_phase, w_scal, out_scal, out_phase};
+  rc = table_run_core(t, ntask, t->mz.as<double>(), t->mrel.as<double>(), nmode, t->wphase.as<double>(),
+                      w_scal ? t->wscal.as<double>() : nullptr, flags, t->out_scal.as<double>(), t->out_phase.as<double>(), nullptr,
+                      nullptr, false, &hio, t->c_ratio.as<double>());
   if (rc) return rc;
   return fetch_stats(t);
 }

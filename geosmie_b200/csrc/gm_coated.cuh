@@ -20,22 +20,30 @@ __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_doub
 __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ double2 cscale(double2 a, double s) { return make_double2(a.x * s, a.y * s); }
 
-// scratch per particle: (nmax+1) * 16 doubles, particle i at soff[i]*16
+// scratch per particle: (nmax+1) * 8 doubles, particle i at soff[i]*8 (+ task * scratch_stride)
+// mat_stride: 0 one material pair for all, 1 per particle, 2 per task (blockIdx.y).
+// core_ratio != NULL (table mode): the core size parameter is core_ratio[task] * y (RH-dependent shell growth).
 __global__ void __launch_bounds__(64) k_coated_coeff(int n, const double* __restrict__ xcore, const double* __restrict__ yshell,
                                                      const double2* __restrict__ m1a, const double2* __restrict__ m2a, int mat_stride,
                                                      const int* __restrict__ nmax, const long long* __restrict__ soff,
                                                      double* __restrict__ scratch, const long long* __restrict__ aboff,
-                                                     double4* __restrict__ ab) {
+                                                     double4* __restrict__ ab, const double* __restrict__ core_ratio,
+                                                     long long scratch_stride, long long ab_stride) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
-  const double x = xcore[p], y = yshell[p];
-  const double2 m1 = m1a[mat_stride ? p : 0], m2 = m2a[mat_stride ? p : 0];
+  const int task = blockIdx.y;
+  const double y = yshell[p];
+  const double x = core_ratio ? core_ratio[task] * y : xcore[p];
+  const int mi = mat_stride == 1 ? p : (mat_stride == 2 ? task : 0);
+  const double2 m1 = m1a[mi], m2 = m2a[mi];
   const int nm = nmax[p];
+  scratch += (size_t)task * scratch_stride;
+  ab += (size_t)task * ab_stride;
   const double2 m = cdiv(m2, m1);                 // :197
   const double2 u = cscale(m1, x), v = cscale(m2, x), w = cscale(m2, y);   // :198-200
   const double mx = fmax(hypot(m1.x * y, m1.y * y), hypot(w.x, w.y));       // :203
   const int nmx = (int)rint(fmax((double)nm, mx) + 16.0);                   // :204
-  double* sc = scratch + (size_t)soff[p] * 16;
+  double* sc = scratch + (size_t)soff[p] * 8;
   double2* Du = reinterpret_cast<double2*>(sc);
   double2* Dv = Du + (nm + 1);
   double2* Dw = Dv + (nm + 1);

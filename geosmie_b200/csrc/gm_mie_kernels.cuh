@@ -155,12 +155,14 @@ struct CoeffArgs {
   double* scal_part;     // [ntask][nmode][ngroup][GM_NSCAL]
   // ---- natural mode / optional per-particle outputs
   const long long* aboff;  // prefix sum of nmax
-  double4* ab;             // [sum nmax] a_n, b_n
+  double4* ab;             // [sum nmax] a_n, b_n (MODE 1: output; MODE 2: input, + task * ab_stride)
+  long long ab_stride;
   double* q;               // [ntask][nx][6] (nullable)
   unsigned long long* stats;  // [0] evals [1] sum nmax [2] sum nmx [3] padded k4 steps
 };
 
-// MODE 0: DMMA group layout (c+ = (a+b) f_n sqrt(w), c- = (a-b) f_n sqrt(w)); MODE 1: natural a_n, b_n.
+// MODE 0: DMMA group layout (c+ = (a+b) f_n sqrt(w), c- = (a-b) f_n sqrt(w)); MODE 1: natural a_n, b_n;
+// MODE 2: like MODE 0 but a_n, b_n are READ from the natural layout (coated spheres, produced by k_coated_coeff).
 template <int MODE>
 __global__ void __launch_bounds__(128, 3) k_coeff(CoeffArgs A) {
   const int g = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -175,9 +177,10 @@ __global__ void __launch_bounds__(128, 3) k_coeff(CoeffArgs A) {
   const double2 mzv = A.mz[mi];
   const double2 mrv = A.mrel[mi];
 
+  constexpr bool TABLE = (MODE != 1);
   double wp = 1.0;
   bool any = true;
-  if (MODE == 0) {
+  if (TABLE) {
     wp = valid ? A.wphase[(size_t)task * A.nx + i] : 0.0;
     any = wp != 0.0;
     if (A.wscal)
@@ -185,10 +188,10 @@ __global__ void __launch_bounds__(128, 3) k_coeff(CoeffArgs A) {
   }
   const bool act = valid && (MODE == 1 || A.dense || any);
   const double2 z = make_double2(mzv.x * xi, mzv.y * xi);                     // mie_coeffs.py:96
-  const int nmx = act ? (int)rint(fmax((double)nm, hypot(z.x, z.y)) + 16.0) : 0;  // mie_coeffs.py:101
+  const int nmx = (act && MODE != 2) ? (int)rint(fmax((double)nm, hypot(z.x, z.y)) + 16.0) : 0;  // mie_coeffs.py:101
   const int J = __reduce_max_sync(0xffffffffu, nmx);
   int rows = 0;
-  if (MODE == 0) {
+  if (TABLE) {
     rows = 4 * A.gk4[g];
     const bool gactive = __any_sync(0xffffffffu, act);
     if (lane == 0) A.gact[(size_t)task * A.ngroup + g] = gactive ? 1 : 0;
@@ -202,10 +205,11 @@ __global__ void __launch_bounds__(128, 3) k_coeff(CoeffArgs A) {
   const double2 zinv = crcp(z);
   const double2 minv = crcp(mrv);
   const double xinv = 1.0 / xi;
-  const double sw = (MODE == 0 && A.scale_sqrtw) ? sqrt(wp) : 1.0;
+  const double sw = (TABLE && A.scale_sqrtw) ? sqrt(wp) : 1.0;
   double* crow = nullptr;
-  if (MODE == 0) crow = A.coef + (size_t)task * A.task_stride + (size_t)A.grow[g] * GM_SB + 2 * lane;
-  const long long abo = (MODE == 1 && valid) ? A.aboff[i] : 0;
+  if (TABLE) crow = A.coef + (size_t)task * A.task_stride + (size_t)A.grow[g] * GM_SB + 2 * lane;
+  const long long abo = (MODE != 0 && valid) ? A.aboff[i] : 0;
+  const double4* ab_in = (MODE == 2) ? A.ab + (size_t)task * A.ab_stride : nullptr;
 
   double2 D = make_double2(0.0, 0.0);
   double psi_n = 0.0, chi_n = 0.0;
@@ -217,7 +221,7 @@ __global__ void __launch_bounds__(128, 3) k_coeff(CoeffArgs A) {
   double qpsi[PD], qchi[PD];
 #pragma unroll
   for (int k = 0; k < PD; ++k) qpsi[k] = qchi[k] = 0.0;
-  if (act) {
+  if (act && MODE != 2) {
     psi_n = A.psi[bbase + (size_t)nm * 32];
     chi_n = A.chi[bbase + (size_t)nm * 32];
 #pragma unroll
@@ -231,7 +235,7 @@ __global__ void __launch_bounds__(128, 3) k_coeff(CoeffArgs A) {
   // ---- phase 1: orders above every particle of the group: only the logarithmic-derivative recurrence
   // mie_coeffs.py:119-121, D_n = r - 1/(D_{n+1} + r), r = (n+1)/z, started from D_{nmx} = 0
   int nstart = J - 1;
-  const int nemit = (MODE == 0) ? rows : __reduce_max_sync(0xffffffffu, act ? nm : 0);
+  const int nemit = TABLE ? rows : __reduce_max_sync(0xffffffffu, act ? nm : 0);
   if (nemit > nstart) nstart = nemit;
   int n = nstart;
   for (; n > nemit; --n) {
@@ -252,27 +256,36 @@ __global__ void __launch_bounds__(128, 3) k_coeff(CoeffArgs A) {
     }
     double2 cp = make_double2(0.0, 0.0), cm = make_double2(0.0, 0.0);
     if (act && n <= nm) {
-      const double psi_m = qpsi[0], chi_m = qchi[0];        // order n-1
-#pragma unroll
-      for (int k = 0; k + 1 < PD; ++k) {
-        qpsi[k] = qpsi[k + 1];
-        qchi[k] = qchi[k + 1];
-      }
-      if (n - 1 - PD >= 0) {
-        qpsi[PD - 1] = A.psi[bbase + (size_t)(n - 1 - PD) * 32];
-        qchi[PD - 1] = A.chi[bbase + (size_t)(n - 1 - PD) * 32];
-      }
+      double2 an, bn;
       const double dn = (double)n;
-      const double nox = dn * xinv;
-      double2 da = cmul(D, minv);                             // mie_coeffs.py:124
-      da.x += nox;
-      double2 db = cmul(D, mrv);                              // mie_coeffs.py:125
-      db.x += nox;
-      // a_n = (da psi_n - psi_{n-1}) / (da xi_n - xi_{n-1}),  xi = psi - i chi      (mie_coeffs.py:113-114,127-128)
-      const double2 an = cdiv(make_double2(fma(da.x, psi_n, -psi_m), da.y * psi_n),
-                              make_double2(fma(da.x, psi_n, fma(da.y, chi_n, -psi_m)), fma(da.y, psi_n, fma(-da.x, chi_n, chi_m))));
-      const double2 bn = cdiv(make_double2(fma(db.x, psi_n, -psi_m), db.y * psi_n),
-                              make_double2(fma(db.x, psi_n, fma(db.y, chi_n, -psi_m)), fma(db.y, psi_n, fma(-db.x, chi_n, chi_m))));
+      if (MODE == 2) {
+        const double4 v = ab_in[abo + n - 1];
+        an = make_double2(v.x, v.y);
+        bn = make_double2(v.z, v.w);
+      } else {
+        const double psi_m = qpsi[0], chi_m = qchi[0];        // order n-1
+#pragma unroll
+        for (int k = 0; k + 1 < PD; ++k) {
+          qpsi[k] = qpsi[k + 1];
+          qchi[k] = qchi[k + 1];
+        }
+        if (n - 1 - PD >= 0) {
+          qpsi[PD - 1] = A.psi[bbase + (size_t)(n - 1 - PD) * 32];
+          qchi[PD - 1] = A.chi[bbase + (size_t)(n - 1 - PD) * 32];
+        }
+        const double nox = dn * xinv;
+        double2 da = cmul(D, minv);                             // mie_coeffs.py:124
+        da.x += nox;
+        double2 db = cmul(D, mrv);                              // mie_coeffs.py:125
+        db.x += nox;
+        // a_n = (da psi_n - psi_{n-1}) / (da xi_n - xi_{n-1}),  xi = psi - i chi      (mie_coeffs.py:113-114,127-128)
+        an = cdiv(make_double2(fma(da.x, psi_n, -psi_m), da.y * psi_n),
+                  make_double2(fma(da.x, psi_n, fma(da.y, chi_n, -psi_m)), fma(da.y, psi_n, fma(-da.x, chi_n, chi_m))));
+        bn = cdiv(make_double2(fma(db.x, psi_n, -psi_m), db.y * psi_n),
+                  make_double2(fma(db.x, psi_n, fma(db.y, chi_n, -psi_m)), fma(db.y, psi_n, fma(-db.x, chi_n, chi_m))));
+        psi_n = psi_m;
+        chi_n = chi_m;
+      }
       // efficiencies, mie_props.py:41-65
       const double cn = 2.0 * dn + 1.0;
       const double rn1 = fast_rcp(dn + 1.0);
@@ -286,9 +299,7 @@ __global__ void __launch_bounds__(128, 3) k_coeff(CoeffArgs A) {
               c2n * (an.x * bn.x + an.y * bn.y);
       a_next = an;
       b_next = bn;
-      psi_n = psi_m;
-      chi_n = chi_m;
-      if (MODE == 0) {
+      if (TABLE) {
         const double f = c2n * sw;
         cp = make_double2((an.x + bn.x) * f, (an.y + bn.y) * f);
         cm = make_double2((an.x - bn.x) * f, (an.y - bn.y) * f);
@@ -296,7 +307,7 @@ __global__ void __launch_bounds__(128, 3) k_coeff(CoeffArgs A) {
         A.ab[abo + n - 1] = make_double4(an.x, an.y, bn.x, bn.y);
       }
     }
-    if (MODE == 0) {
+    if (TABLE) {
       double* r = crow + (size_t)(n - 1) * GM_SB;
       *reinterpret_cast<double2*>(r) = cp;
       *reinterpret_cast<double2*>(r + 64) = cm;
@@ -326,10 +337,10 @@ __global__ void __launch_bounds__(128, 3) k_coeff(CoeffArgs A) {
       atomicAdd(&A.stats[0], (unsigned long long)ne);
       atomicAdd(&A.stats[1], (unsigned long long)snm);
       atomicAdd(&A.stats[2], (unsigned long long)snx);
-      if (MODE == 0) atomicAdd(&A.stats[3], (unsigned long long)A.gk4[g]);
+      if (TABLE) atomicAdd(&A.stats[3], (unsigned long long)A.gk4[g]);
     }
   }
-  if (MODE == 0) {
+  if (TABLE) {
     // size-distribution scalar sums as warp-shuffle reductions (dointegration.py:1104-1107, :1133-1190)
     const double x2 = xi * xi, x3 = x2 * xi, x4 = x2 * x2;
     for (int k = 0; k < A.nmode; ++k) {

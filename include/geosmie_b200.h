@@ -110,6 +110,16 @@ int gm_table_run(gm_table_t t, int ntask, const double* mz, const double* mrel, 
 int gm_table_run_dev(gm_table_t t, int ntask, const double* mz, const double* mrel, int nmode, const double* w_phase,
                      const double* w_scal, int flags, double* out_scal, double* out_phase);
 /*
+ * gm_table_run_coated: like gm_table_run for coated (core + shell) spheres -- the table's x grid is the SHELL size
+ * parameter y, task i has core index m1[i], shell index m2[i] (both sqrt(eps), as in gm_mie_eval) and core size
+ * parameter core_ratio[i] * y (RH-dependent shell growth: core_ratio = 1 / growth factor).  Coefficients follow
+ * coated_mie_coeff (mie_coeffs.py:183-251); the contraction, Mueller and size-distribution stages are shared with the
+ * homogeneous path.  Extension: the reference has no coated table driver (mie_coated.py:80 is a dead branch).
+ */
+int gm_table_run_coated(gm_table_t t, int ntask, const double* m1, const double* m2, const double* core_ratio, int nmode,
+                        const double* w_phase, const double* w_scal, int flags, double* out_scal, double* out_phase);
+
+/*
  * gm_table_run_psd: like gm_table_run, but the number weights are generated on the device from per-(task, mode)
  * parameters (replaces the O(nx) numpy work of dointegration.calculatePSD :539-664 / particleparams.getLogNormPSD
  * :113-127; the scalars below are still derived on the host with the reference's formulas):
