@@ -36,6 +36,9 @@ METRIC = "mie_particle_evals_per_sec"
 UNIT = "particle-evals/s"
 NANG = 371
 FP64_PEAK_TFLOPS = 37.1   # measured on this pool's B200 with tools/fp64_peak.cu (DMMA m8n8k4), profiles/r01_fp64_peak.json
+# dram__bytes_read.sum + dram__bytes_write.sum of k_contract per SU cell, from the `ncu --set full` capture
+# profiles/r01_contract_su_63cells.ncu-rep (83.54 MB + 13.58 MB over 63 dense cells)
+CONTRACT_DRAM_BYTES_PER_CELL = (83.544832e6 + 13.583616e6) / 63
 
 
 def build_su_plan():
@@ -289,7 +292,10 @@ def main():
                 "d2h_bytes_per_step": int(scal_h.numel() * 8 + phase_h.numel() * 8 + coef_h.numel() * 8)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "k_contract<false> (FP64 DMMA m8n8k4)", "achieved": ach, "peak": FP64_PEAK_TFLOPS,
-                     "unit": "TFLOP/s", "frac": (ach / FP64_PEAK_TFLOPS) if ach else None, "traffic": None,
+                     "unit": "TFLOP/s", "frac": (ach / FP64_PEAK_TFLOPS) if ach else None,
+                     "traffic": CONTRACT_DRAM_BYTES_PER_CELL * ncell,
+                     "traffic_note": "DRAM bytes of the k_contract launches of one step, scaled per cell from the ncu capture in "
+                                     "profiles/ (algorithmic: 32 B x sum(nmax) coefficient stream = %.2e B)" % (32.0 * float(np.sum(plan.nmax)) * ncell),
                      "peak_source": "measured on this pool: tools/fp64_peak.cu DMMA burst 37.1 TFLOP/s (MEASURED_PEAKS.json has "
                                     "no FP64 entry; nominal 37 TFLOP/s)",
                      "flop_per_launch_set": contract_flop, "kernel_ms_per_step": kms,
