@@ -446,7 +446,7 @@ class BinPlan(object):
         self.psd_kind = None
         mr_l, w_l, par_l, meta = [], [], [], []
         want = None if cells is None else set(cells)
-        if device_psd and want is not None:
+        if device_psd and want:
             want |= {(li, 0) for (li, _) in want}      # reff_mass0 comes from the RH-index-0 cell of the same wavelength
         for li, lam in enumerate(lambarr):
             if want is not None and not any(c[0] == li for c in want):
@@ -548,11 +548,13 @@ def run_bin(plan, costarr, handle=None, elide=True, table=None):
     return ret, table
 
 
-def fun(partID0, datatype, oppfx, oppclassic, elide=True, write=True, comm=None, device_psd=True):
+def fun(partID0, datatype, oppfx, oppclassic, elide=True, write=True, comm=None, device_psd=True, keep_phase=True):
     """Main table build called from runoptics.py (dointegration.py:672-1036).  Same arguments as the reference plus
     `elide` (skip exactly-zero-weight particles; result-neutral), `write` (False: return the arrays only), `comm`
     (a geosmie_b200.dist.Comm: cells are sharded across ranks and gathered to rank 0) and `device_psd` (True: number
-    weights generated on the GPU from per-cell parameters; False: numpy weights exactly like calculatePSD, uploaded).  Returns the dict of arrays
+    weights generated on the GPU from per-cell parameters; False: numpy weights exactly like calculatePSD, uploaded);
+    `keep_phase=False` (only with write=False) drops the six [bin, wavelength, rh, ang] arrays from the result -- for
+    fine spectral grids whose only consumer is the band averaging (pback is still filled).  Returns the dict of arrays
     written to optics_<id>.nomom[.legacy].nc4 on rank 0 (None elsewhere)."""
     partID = partID0.split('/')[-1].replace(".json", "")
     print("\n ####################\n Starting case %s\n ####################\n" % partID)
@@ -580,67 +582,71 @@ def fun(partID0, datatype, oppfx, oppclassic, elide=True, write=True, comm=None,
         rh_used[np.where(rh_used > params['maxrh'])[0]] = params['maxrh']
     nb, nl, nr, na = len(radiusarr), len(lambarr), len(rh), len(ang)
     vals = {}
+    if not keep_phase and write:
+        raise ValueError("keep_phase=False needs write=False (the file layout contains the phase matrices)")
     for key in allkeys:
+        if not keep_phase and key in scatkeys:
+            continue
         shape = {"scat": (nb, nl, nr, na), "ele": (nb, nl, nr, 6), "nl": (nb, nr), "scal": (nb, nl, nr)}[_kind_of(key)]
         vals[key] = np.zeros(shape)
 
     rank, world = (0, 1) if comm is None else (comm.rank, comm.world)
+    keys = list(vals.keys())
+    width = {k: {"scat": na, "ele": 6}.get(_kind_of(k), 1) for k in keys}
     for radind in radindarr:
         print("=== === === USING RADIND %d" % radind)
         trivial = params['rhDep']['type'] == 'trivial'
-        all_cells = [(li, rhi) for li in range(nl) for rhi in range(nr) if not (trivial and rhi > 0)]
-        mine = all_cells[rank::world] if world > 1 else None
-        if mine is not None and device_psd:
-            # keep the RH-index-0 cell of every wavelength on the rank that owns any of its cells (needed for reff_mass0
-            # only after the gather, so sharding stays a plain round-robin): rank r takes wavelengths r, r+W, ...
-            mine = [c for c in all_cells if c[0] % world == rank]
+        # Multi-GPU: rank r owns the wavelengths r, r+W, ... with all their RH cells (the RH-index-0 cell that defines
+        # mass0 / reff_mass0 stays local), reduces and post-processes them, and only finished rows travel to rank 0.
+        mine = None if world == 1 else [(li, rhi) for li in range(rank, nl, world) for rhi in range(nr) if not (trivial and rhi > 0)]
         plan = BinPlan(params, radind, lambarr, rh_used, part_m, water_m, cells=mine, device_psd=device_psd)
-        table = _lib.Table(plan.xx, plan.nmax, costarr)
-        scal, phase, tpc = plan.evaluate(table, elide=elide)
-        table.close()
-        if comm is not None and world > 1:
-            gathered = comm.gather_cells(scal, phase)
+        ncell = len(plan.cells)
+        li = np.array([c[0] for c in plan.cells], dtype=np.int64)
+        ri = np.array([c[1] for c in plan.cells], dtype=np.int64)
+        rows = np.zeros((ncell, 2 + sum(width.values())))
+        if ncell:
+            table = _lib.Table(plan.xx, plan.nmax, costarr)
+            scal, phase, tpc = plan.evaluate(table, elide=elide)
+            table.close()
+            ret = postprocess(plan.reduce(scal, phase, tpc), ang)
+            # mass0 = volume(RH index 0) * rhop0 of the same (bin, lambda) (dointegration.py:992-997)
+            vol0 = np.zeros(nl)
+            sel0 = ri == 0
+            vol0[li[sel0]] = ret['volume'][sel0]
+            mass0 = vol0[li] * plan.rhop0
+            ret['area'] = ret['area'] / mass0
+            ret['volume'] = ret['volume'] / mass0
+            ret['rhop'] = plan.rhop
+            ret['growth_factor'] = plan.gf
+            ret['rLow'] = plan.rLow
+            ret['rUp'] = plan.rUp
+            ret['refreal'] = plan.m[:, 0].real
+            ret['refimag'] = -np.abs(plan.m[:, 0].imag)
+            rows[:, 0], rows[:, 1] = li, ri
+            o = 2
+            for k in keys:
+                rows[:, o:o + width[k]] = np.asarray(ret[k]).reshape(ncell, width[k])
+                o += width[k]
+        if world > 1:
+            rows = comm.gather_rows(rows)          # NCCL gather over NVLink (gloo on CPU)
             if rank != 0:
                 continue
-            # rank r holds all_cells[r::world]; rebuild the full bin plan metadata on rank 0
-            full = BinPlan(params, radind, lambarr, rh_used, part_m, water_m, cells=None, device_psd=device_psd)
-            if device_psd:
-                order = [c for r in range(world) for c in all_cells if c[0] % world == r]
-            else:
-                order = [c for r in range(world) for c in all_cells[r::world]]
-            pos = {c: i for i, c in enumerate(order)}
-            idx = np.array([pos[c] for c in full.cells])
-            tsel = (idx[:, None] * tpc + np.arange(tpc)[None, :]).reshape(-1)
-            scal, phase = gathered[0][tsel], gathered[1][tsel]
-            plan = full
-        ret = plan.reduce(scal, phase, tpc)
-        ret = postprocess(ret, ang)
-        li = np.array([c[0] for c in plan.cells])
-        ri = np.array([c[1] for c in plan.cells])
-        # mass0 = volume(RH index 0) * rhop0 of the same (bin, lambda) (dointegration.py:992-997)
-        vol0 = np.zeros(nl)
-        sel0 = ri == 0
-        vol0[li[sel0]] = ret['volume'][sel0]
-        mass0 = vol0[li] * plan.rhop0
-        ret['area'] = ret['area'] / mass0
-        ret['volume'] = ret['volume'] / mass0
-        ret['rhop'] = plan.rhop
-        ret['growth_factor'] = plan.gf
-        ret['rLow'] = plan.rLow
-        ret['rUp'] = plan.rUp
-        ret['refreal'] = plan.m[:, 0].real
-        ret['refimag'] = -np.abs(plan.m[:, 0].imag)
-        for key in allkeys:
-            kind = _kind_of(key)
-            if kind == "nl":
+            li, ri = rows[:, 0].astype(np.int64), rows[:, 1].astype(np.int64)
+        o = 2
+        for key in keys:
+            col = rows[:, o:o + width[key]]
+            o += width[key]
+            if _kind_of(key) == "nl":
                 # (bin, rh) variables are overwritten at every wavelength: the last one wins (dointegration.py:1026-1027)
                 last = li == li.max()
-                vals[key][radind, ri[last]] = ret[key][last]
+                vals[key][radind, ri[last]] = col[last, 0]
+            elif width[key] == 1:
+                vals[key][radind, li, ri] = col[:, 0]
             else:
-                vals[key][radind, li, ri] = ret[key]
+                vals[key][radind, li, ri] = col
         if trivial:
             # copyDryValues (dointegration.py:465-491)
-            for key in allkeys:
+            for key in vals:
                 if _kind_of(key) == "nl":
                     vals[key][radind, 1:] = vals[key][radind, 0]
                 else:

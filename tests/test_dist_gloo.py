@@ -28,6 +28,11 @@ if comm.rank == 0:
     s, p = out[0][pos], out[1][pos]
     ok = all(s[i, 0, 0] == li * 100 + rhi and p[i, 2, 5] == li + 0.001 * rhi + 2 for i, (li, rhi) in enumerate(cells))
     print("GATHER_OK" if ok and s.shape == (35, 1, 11) and p.shape == (35, 4, 13) else "GATHER_BAD")
+# ragged gather as used by dointegration.fun (finished rows; a rank may own no wavelength at all)
+rows = np.full((3, 5), float(comm.rank)) if comm.rank == 0 else np.zeros((0, 5))
+g = comm.gather_rows(rows)
+if comm.rank == 0:
+    print("RAGGED_OK" if g.shape == (3, 5) and np.all(g == 0.0) else "RAGGED_BAD")
 comm.close()
 """
 
@@ -58,3 +63,4 @@ def test_gloo_world2_gather(tmp_path):
     outs = [p.communicate(timeout=240)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "GATHER_OK" in outs[0], outs
+    assert "RAGGED_OK" in outs[0], outs

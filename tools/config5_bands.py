@@ -1,0 +1,58 @@
+#!/usr/bin/env python3
+"""BASELINE config 5: RRTMG band-averaged tables from a FINE spectral grid (2048 wavelengths instead of 61) for the
+species tables, cells sharded across the GPUs of one box (torchrun) and gathered to rank 0 with NCCL, then band-averaged.
+
+    python tools/config5_bands.py [su bc ss] [--nlam 2048]
+    torchrun --nproc-per-node 8 tools/config5_bands.py su bc ss
+The refractive-index spectra are the species tables resampled to N log-spaced wavelengths by linear interpolation (what
+interp1d would return).  SS keeps no phase matrices on the host (6.5 GB at 2048 wavelengths)."""
+import json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+from helpers import run_dir
+from geosmie_b200 import bandaverage, dointegration as DI, workloads
+
+nlam = int(sys.argv[sys.argv.index("--nlam") + 1]) if "--nlam" in sys.argv else 2048
+species = [a for a in sys.argv[1:] if a in ("su", "bc", "ss")] or ["su", "bc", "ss"]
+world = int(os.environ.get("WORLD_SIZE", "1"))
+comm = None
+if world > 1:
+    from geosmie_b200 import dist
+    comm = dist.Comm.from_env()
+rank = 0 if comm is None else comm.rank
+
+g = np.load(workloads.DEFAULT_FIXTURE)
+for sp in species:
+    ml = g[sp + "__mlist"]
+    lam = np.geomspace(ml[0][0], ml[0][-1], nlam)
+    lam[0], lam[-1] = ml[0][0], ml[0][-1]
+    n, k = np.interp(lam, ml[0], ml[1]), np.interp(lam, ml[0], ml[2])
+    cfg = json.loads(json.dumps(workloads.SPECIES[sp]))
+    cfg.pop("hydrophobic", None)
+    cfg["ri"] = {"format": "wsv", "path": ["ri-%s-fine.wsv" % sp]}
+    files = {sp + "_fine.json": json.dumps(cfg),
+             "ri-%s-fine.wsv" % sp: "\n".join("%.17g %.17g %.17g" % (l * 1e6, a, b) for l, a, b in zip(lam, n, k)) + "\n"}
+    with run_dir(files) as d:
+        if comm is not None:
+            comm.barrier()
+        t0 = time.time()
+        sys.stdout = open(os.devnull, "w")
+        out = DI.fun(sp + "_fine.json", "json", d, False, write=False, comm=comm, keep_phase=(sp != "ss"))
+        sys.stdout = sys.__stdout__
+        t1 = time.time()
+        if rank == 0:
+            vals = out["vals"]
+            lo, up, mean, usewn, nb = bandaverage.getBands("RRTMG")
+            res = {}
+            for var in bandaverage.varsToAverage:
+                a = vals[var].transpose(0, 2, 1)                      # (bin, rh, lambda)
+                nbin, nrh = a.shape[:2]
+                res[var] = bandaverage.average_columns(out["wavelength"], a.reshape(nbin * nrh, -1), "RRTMG").reshape(nbin, nrh, -1)
+            t2 = time.time()
+            ncell = vals["qext"].size
+            print(json.dumps({"config": 5, "species": sp, "n_lambda": nlam, "n_gpus": world, "cells": int(ncell),
+                              "table_s": t1 - t0, "bands_s": t2 - t1, "qext_band_mean": float(np.mean(res["qext"])),
+                              "finite": bool(all(np.all(np.isfinite(v)) for v in res.values()))}), flush=True)
+if comm is not None:
+    comm.close()

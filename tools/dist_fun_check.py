@@ -10,7 +10,7 @@ from geosmie_b200 import dist, dointegration as DI
 
 comm = dist.Comm.from_env()
 ok = True
-for name in ("su_mini", "ss_mini", "mm_mini"):
+for name in ("su_mini", "ss_mini", "mm_mini", "bc_mini"):
     for device_psd in (True, False):
         g, files, base = fun_fixture(name)
         with run_dir(files) as d:
