@@ -225,13 +225,12 @@ def main():
     mz_hn, w_hn = mz_h.numpy(), w_h.numpy()          # views of the pinned host buffers
     scal_hn, phase_hn = scal_h.numpy(), phase_h.numpy()
 
+    coef_hn = coef_h.numpy()
+
     def step_e2e():
-        # the user-facing call with HOST buffers (gm_table_run): H2D of this step's inputs, kernels and D2H of the results,
-        # pipelined batch by batch inside the library; then the GSF expansion of the device copy and D2H of the moments
+        # the user-facing call with HOST buffers (gm_table_run_psd with the fused GSF stage): H2D of this step's inputs,
+        # kernels, and D2H of the reduced sums and GSF moments pipelined batch by batch inside the library
         table.run_psd(mz_psd, mz_psd, psd_kind, psd_par, psd_frac, elide=False, out=(scal_hn, phase_hn))
-        _, ph_ptr = table.device_outputs()
-        h.gsf_expand_phase4_dev(ang, ncell, ph_ptr, coef_d.data_ptr(), cn_d.data_ptr())
-        coef_h.copy_(coef_d, non_blocking=True)
         if world > 1:
             torch.cat([scal_d.reshape(ncell, -1), phase_d.reshape(ncell, -1), coef_d.reshape(ncell, -1)], dim=1, out=packed)
             td.gather(packed, gather_buf, dst=0)
@@ -267,9 +266,11 @@ def main():
     launches = (h.launch_count() - launches0) // args.steps
     kms = table.last_kernel_ms()            # CUDA events around the launches of the LAST timed step
     stats = table.last_stats()
+    table.set_gsf(ang, 129, False, coef_hn, None)
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
+    table.set_gsf(None)
     clocks = sampler.stop() if rank == 0 else None
 
     total_evals = float(ncell) * nx * world
@@ -288,7 +289,7 @@ def main():
                    "parallelism": "cells sharded, %d rank(s), NCCL gather to rank 0" % world},
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(mz_psd.nbytes * 2 + psd_par.nbytes + psd_frac.nbytes),
-                "api": "gm_table_run_psd (host buffers: per-cell m and PSD parameters in, reduced sums out) + gm_gsf_expand_phase4_dev",
+                "api": "gm_table_run_psd with the fused GSF stage (host buffers: per-cell m and PSD parameters in, reduced sums and GSF moments out)",
                 "d2h_bytes_per_step": int(scal_h.numel() * 8 + phase_h.numel() * 8 + coef_h.numel() * 8)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "k_contract<false> (FP64 DMMA m8n8k4)", "achieved": ach, "peak": FP64_PEAK_TFLOPS,

@@ -39,6 +39,8 @@ SIGNATURES = {
     "gm_table_run": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int, vp, vp]),
     "gm_table_run_dev": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int, vp, vp]),
     "gm_table_run_coated": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, C.c_int, vp, vp]),
+    "gm_table_set_gsf": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp]),
+    "gm_table_gsf_device": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp)]),
     "gm_table_set_dr": (C.c_int, [vp, vp]),
     "gm_table_run_psd": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp]),
     "gm_table_get_weights": (C.c_int, [vp, C.c_int, C.c_int, vp]),
@@ -242,6 +244,18 @@ class Table:
         check(self.lib.gm_table_run_coated(self.t, ntask, ptr(m1), ptr(m2), ptr(ratio), nmode, ptr(wp), ptr(ws),
                                            F_ELIDE_ZERO_WEIGHT if elide else 0, ptr(scal), ptr(phase)))
         return scal, phase
+
+    def set_gsf(self, ang_deg, ng=129, quantize10=False, coef_out=None, cnorm_out=None):
+        """Fuse the GSF moment expansion into the following run calls; coef_out [ntask][6][ng] (ideally pinned) receives
+        the moments.  set_gsf(None) switches the stage off."""
+        if ang_deg is None:
+            check(self.lib.gm_table_set_gsf(self.t, None, 0, 0, None, None))
+            self._gsf_keep = None
+            return
+        ang = f64(ang_deg)
+        assert ang.size == self.nang
+        self._gsf_keep = (ang, coef_out, cnorm_out)
+        check(self.lib.gm_table_set_gsf(self.t, ptr(ang), int(ng), int(bool(quantize10)), ptr(coef_out), ptr(cnorm_out)))
 
     def set_dr(self, dr):
         check(self.lib.gm_table_set_dr(self.t, ptr(f64(dr))))

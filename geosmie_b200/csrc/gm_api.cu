@@ -273,6 +273,12 @@ struct gm_table_s {
   std::vector<int32_t> hnmax;
   DevBuf T, cost, dr, psd_par, psd_frac;
   DevBuf c_ab, c_scratch, c_soff, c_aboff, c_ratio;   // coated-sphere table path
+  // fused GSF stage (gm_table_set_gsf): moments of every finished batch are expanded and downloaded behind the kernels
+  std::vector<double> gsf_ang;
+  int gsf_ng = 0, gsf_quant = 0;
+  double* gsf_coef_host = nullptr;
+  double* gsf_cnorm_host = nullptr;
+  DevBuf gsf_coef, gsf_cnorm;
   long long c_nab = 0, c_nscr = 0;
   bool have_dr = false;
   bool psd_separate = false;
@@ -327,7 +333,7 @@ extern "C" int gm_table_destroy(gm_table_t t) {
   if (!t) return GM_OK;
   cudaSetDevice(t->h->device);
   t->D.release();
-  for (DevBuf* b : {&t->c_ab, &t->c_scratch, &t->c_soff, &t->c_aboff, &t->c_ratio, &t->dr, &t->psd_par, &t->psd_frac, &t->T, &t->cost, &t->coef, &t->gact, &t->scal_part, &t->part, &t->chunk_start, &t->mz, &t->mrel, &t->wphase,
+  for (DevBuf* b : {&t->gsf_coef, &t->gsf_cnorm, &t->c_ab, &t->c_scratch, &t->c_soff, &t->c_aboff, &t->c_ratio, &t->dr, &t->psd_par, &t->psd_frac, &t->T, &t->cost, &t->coef, &t->gact, &t->scal_part, &t->part, &t->chunk_start, &t->mz, &t->mrel, &t->wphase,
                     &t->wscal, &t->out_scal, &t->out_phase, &t->stats, &t->q, &t->s12})
     b->release();
   for (auto& e : t->evpool) cudaEventDestroy(e);
@@ -473,6 +479,9 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
       (rc = t->part.ensure(sizeof(double) * (size_t)tb * nchunk * 4 * GM_NANG_PAD)) ||
       (rc = t->chunk_start.ensure(sizeof(int) * (nchunk + 1))) || (rc = t->stats.ensure(sizeof(unsigned long long) * 8)))
     return rc;
+  if (t->gsf_ng > 0 && !per_particle) {
+    if ((rc = t->gsf_coef.ensure(sizeof(double) * (size_t)ntask * 6 * t->gsf_ng)) || (rc = t->gsf_cnorm.ensure(sizeof(double) * ntask))) return rc;
+  }
   GM_CUDA_TRY(cudaMemcpyAsync(t->chunk_start.p, cstart.data(), sizeof(int) * (nchunk + 1), cudaMemcpyHostToDevice, st));
   GM_CUDA_TRY(cudaMemsetAsync(t->stats.p, 0, sizeof(unsigned long long) * 8, st));
   const int smem = GM_CONTRACT_SMEM;
@@ -584,6 +593,12 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
                                              d_out_phase + (size_t)t0 * 4 * t->nang, d_out_scal + (size_t)t0 * nmode * GM_NSCAL);
       GM_LAUNCH_CHECK(h);
       if ((rc = ev_mark(t, 2))) return rc;
+      if (t->gsf_ng > 0) {
+        // fused GSF stage on this batch's phase sums (same stream, so it runs right behind k_finalize)
+        rc = gm_gsf_phase4_async(h, nt, t->nang, t->gsf_ang.data(), d_out_phase + (size_t)t0 * 4 * t->nang, t->gsf_ng,
+                                 t->gsf_coef.as<double>() + (size_t)t0 * 6 * t->gsf_ng, t->gsf_cnorm.as<double>() + t0, t->gsf_quant);
+        if (rc) return rc;
+      }
       if (hio) {
         GM_CUDA_TRY(cudaEventRecord(t->io_events[nbatch + bi], st));
         GM_CUDA_TRY(cudaStreamWaitEvent(t->d2h_stream, t->io_events[nbatch + bi], 0));
@@ -591,6 +606,13 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
                                     sizeof(double) * (size_t)nt * nmode * GM_NSCAL, cudaMemcpyDeviceToHost, t->d2h_stream));
         GM_CUDA_TRY(cudaMemcpyAsync(hio->out_phase + (size_t)t0 * 4 * t->nang, d_out_phase + (size_t)t0 * 4 * t->nang,
                                     sizeof(double) * (size_t)nt * 4 * t->nang, cudaMemcpyDeviceToHost, t->d2h_stream));
+        if (t->gsf_ng > 0 && t->gsf_coef_host) {
+          GM_CUDA_TRY(cudaMemcpyAsync(t->gsf_coef_host + (size_t)t0 * 6 * t->gsf_ng, t->gsf_coef.as<double>() + (size_t)t0 * 6 * t->gsf_ng,
+                                      sizeof(double) * (size_t)nt * 6 * t->gsf_ng, cudaMemcpyDeviceToHost, t->d2h_stream));
+          if (t->gsf_cnorm_host)
+            GM_CUDA_TRY(cudaMemcpyAsync(t->gsf_cnorm_host + t0, t->gsf_cnorm.as<double>() + t0, sizeof(double) * nt, cudaMemcpyDeviceToHost,
+                                        t->d2h_stream));
+        }
       }
     }
   }
@@ -686,6 +708,29 @@ extern "C" int gm_table_run_coated(gm_table_t t, int ntask, const double* m1, co
                       nullptr, false, &hio, t->c_ratio.as<double>());
   if (rc) return rc;
   return fetch_stats(t);
+}
+
+extern "C" int gm_table_set_gsf(gm_table_t t, const double* ang_deg, int ng, int quantize10, double* coef_host, double* cnorm_host) {
+  GM_REQUIRE(t != nullptr, "table is NULL");
+  if (ng <= 0 || !ang_deg) {   // switch the fused stage off
+    t->gsf_ng = 0;
+    t->gsf_coef_host = t->gsf_cnorm_host = nullptr;
+    return GM_OK;
+  }
+  GM_REQUIRE(ng >= 3 && ng <= 2048, "ng out of range");
+  t->gsf_ang.assign(ang_deg, ang_deg + t->nang);
+  t->gsf_ng = ng;
+  t->gsf_quant = quantize10;
+  t->gsf_coef_host = coef_host;
+  t->gsf_cnorm_host = cnorm_host;
+  return GM_OK;
+}
+
+extern "C" int gm_table_gsf_device(gm_table_t t, double** coef, double** cnorm) {
+  GM_REQUIRE(t != nullptr, "table is NULL");
+  if (coef) *coef = t->gsf_coef.as<double>();
+  if (cnorm) *cnorm = t->gsf_cnorm.as<double>();
+  return GM_OK;
 }
 
 extern "C" int gm_table_set_dr(gm_table_t t, const double* dr) {

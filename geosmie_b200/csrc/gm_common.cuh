@@ -70,6 +70,10 @@ struct gm_handle_s {
   std::vector<double> gsf_key;
 };
 
+// GSF expansion of gm_table_run's phase layout on device pointers (gm_gsf.cu); asynchronous on the handle's stream
+int gm_gsf_phase4_async(gm_handle_s* h, int ncell, int nang, const double* h_ang_deg, const double* d_P4, int ng, double* d_coef,
+                        double* d_cnorm, int quantize10);
+
 // ------------------------------------------------------------------------------------------------ table geometry
 // Layout constants shared by the coefficient kernel (producer) and the DMMA contraction kernel (consumer).
 constexpr int GM_GROUP = 32;          // particles per group = one warp of the coefficient kernel = DMMA N extent / 2

@@ -251,6 +251,11 @@ extern "C" int gm_gsf_expand_dev(gm_handle_t h, int ncell, int nang, const doubl
   return gsf_core(h, ncell, nang, ang_deg, F, ng, coef, cnorm, quantize10);
 }
 
+int gm_gsf_phase4_async(gm_handle_s* h, int ncell, int nang, const double* h_ang_deg, const double* d_P4, int ng, double* d_coef,
+                        double* d_cnorm, int quantize10) {
+  return gsf_core(h, ncell, nang, h_ang_deg, d_P4, ng, d_coef, d_cnorm, quantize10, 4);
+}
+
 extern "C" int gm_gsf_expand_phase4_dev(gm_handle_t h, int ncell, int nang, const double* ang_deg, const double* P4, int ng,
                                         double* coef, double* cnorm, int quantize10) {
   GM_REQUIRE(h && ang_deg && P4 && coef, "NULL argument");

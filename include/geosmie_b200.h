@@ -138,6 +138,17 @@ int gm_table_run_psd(gm_table_t t, int ntask, const double* mz, const double* mr
 /* the generated weights of the last gm_table_run_psd (host copy, for validation): w [ntask][nmode][nx] */
 int gm_table_get_weights(gm_table_t t, int ntask, int nmode, double* w);
 
+/*
+ * Fused GSF stage: after gm_table_set_gsf every gm_table_run* call also expands the phase sums of each finished batch
+ * of tasks into generalized-spherical-function moments (the work of rungsf.py / gm_gsf_expand) right behind the
+ * reduction kernel, and -- for the host-buffer calls -- downloads them batch by batch while later batches compute.
+ *   ang_deg [nang of the table] scattering angles in degrees; ng moments (129 = NSPHER, params.h:14);
+ *   coef_host [ntask][6][ng] / cnorm_host [ntask] must stay valid for the following run calls (may be NULL: device only,
+ *   see gm_table_gsf_device).  ng = 0 switches the stage off.
+ */
+int gm_table_set_gsf(gm_table_t t, const double* ang_deg, int ng, int quantize10, double* coef_host, double* cnorm_host);
+int gm_table_gsf_device(gm_table_t t, double** coef, double** cnorm);
+
 /* device copies of the outputs of the last host-buffer gm_table_run (valid until the next call on this table), so that
  * gm_gsf_expand_phase4_dev can be chained without a host round trip */
 int gm_table_device_outputs(gm_table_t t, double** out_scal, double** out_phase);
