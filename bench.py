@@ -141,7 +141,7 @@ def run_reference(args):
     plan = build_su_plan()
     vals = []
     for s in range(args.warmup + args.steps):
-        cb, t = cpu_baseline(plan, seconds=4.0)
+        cb, t = cpu_baseline(plan, seconds=float(os.environ.get("GEOSMIE_REF_SECONDS", "4.0")))
         if s >= args.warmup:
             vals.append((cb, t))
     v = float(np.mean([c["value"] for c, _ in vals]))

@@ -163,8 +163,11 @@ struct CoeffArgs {
 
 // MODE 0: DMMA group layout (c+ = (a+b) f_n sqrt(w), c- = (a-b) f_n sqrt(w)); MODE 1: natural a_n, b_n;
 // MODE 2: like MODE 0 but a_n, b_n are READ from the natural layout (coated spheres, produced by k_coated_coeff).
+#ifndef GM_COEFF_MINB
+#define GM_COEFF_MINB 3
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(128, 3) k_coeff(CoeffArgs A) {
+__global__ void __launch_bounds__(128, GM_COEFF_MINB) k_coeff(CoeffArgs A) {
   const int g = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (g >= A.ngroup) return;
   const int lane = threadIdx.x & 31;

@@ -6,14 +6,20 @@ from optparse import OptionParser
 from . import convertncdf
 
 
+# (flag, default, help) -- the option set of the reference CLI (src/gsf/rungsf.py:12-26)
+_OPTIONS = [
+    ("filename", "", "Optical table file to use (default=%s)" % ""),
+    ("dest", ".", "Output directory (default=%s)" % "."),
+    ("mode", "pygeos", "Input file format (default=%s)" % "pygeos"),
+    ("rhop", 1000.0, "Particle density (not needed/used for modes pygeos, legendre) (default=%s)" % 1000.0),
+]
+
+
 def main(argv=None):
     parser = OptionParser(usage="Usage: %prog", version='0.0.1')
-    parser.add_option("--filename", dest="filename", default="", help="Optical table file to use (default=%s)" % (""))
-    parser.add_option("--dest", dest="dest", default=".", help="Output directory (default=%s)" % ("."))
-    parser.add_option("--mode", dest="mode", default="pygeos", help="Input file format (default=%s)" % ("pygeos"))
-    parser.add_option("--rhop", dest="rhop", default=1000.0,
-                      help="Particle density (not needed/used for modes pygeos, legendre) (default=%s)" % (1000.0))
-    (options, args) = parser.parse_args(argv)
+    for name, default, text in _OPTIONS:
+        parser.add_option("--" + name, dest=name, default=default, help=text)
+    options, _ = parser.parse_args(argv)
     if not os.path.exists(options.filename):
         parser.error("Input file path (--filename) does not exist")
     convertncdf.convertFile(options.filename, options.dest, options.mode, options.rhop)

@@ -12,34 +12,45 @@ from . import dointegration, hydrophobic
 from . import particleparams as pp
 
 
-def main(argv=None):
+# (flags, dest, default, help) -- the option set of the reference CLI (src/geosmie/runoptics.py:28-51) plus --dense
+_OPTIONS = [
+    (("--name",), "name", "", "Particle file to use (default=%s)" % ""),
+    (("--namelist",), "namelist", "",
+     "File with list of particle files (to be passed to --file) to run iteratively. If used, overrides --file (default=%s)" % ""),
+    (("--datatype",), "datatype", "json", "Particle data type to use %s (default=%s)" % (['json'], "json")),
+    (("--dest",), "dest", ".", "Output directory to use (default=%s)" % "."),
+]
+_FLAGS = [
+    (("-c", "--classic"), "classic", "write output filename is legacy dimensioning"),
+    (("--dense",), "dense", "also evaluate particles whose size-distribution weight is exactly zero (reference-equivalent work)"),
+]
+
+
+def _parse(argv):
     parser = OptionParser(usage="Usage: %prog", version='0.0.1')
-    acceptedDatatypes = ['json']
-    parser.add_option("--name", dest="name", default="", help="Particle file to use (default=%s)" % (""))
-    parser.add_option("--namelist", dest="namelist", default="",
-                      help="File with list of particle files (to be passed to --file) to run iteratively. If used, overrides --file (default=%s)" % (""))
-    parser.add_option("--datatype", dest="datatype", default="json",
-                      help="Particle data type to use %s (default=%s)" % (acceptedDatatypes, "json"))
-    parser.add_option("--dest", dest="dest", default=".", help="Output directory to use (default=%s)" % ("."))
-    parser.add_option("-c", "--classic", action="store_true", dest="classic", default=False,
-                      help="write output filename is legacy dimensioning")
-    parser.add_option("--dense", action="store_true", dest="dense", default=False,
-                      help="also evaluate particles whose size-distribution weight is exactly zero (reference-equivalent work)")
-    (options, args) = parser.parse_args(argv)
-    if options.datatype not in acceptedDatatypes:
-        parser.error("data type must be one of: %s" % (acceptedDatatypes))
+    for flags, dest, default, text in _OPTIONS:
+        parser.add_option(*flags, dest=dest, default=default, help=text)
+    for flags, dest, text in _FLAGS:
+        parser.add_option(*flags, action="store_true", dest=dest, default=False, help=text)
+    options, _ = parser.parse_args(argv)
+    if options.datatype not in ['json']:
+        parser.error("data type must be one of: %s" % (['json']))
     if not os.path.exists(options.dest):
         parser.error("Output directory (--dest) does not exist")
-    if options.name == "" and options.namelist == "":
+    if not options.name and not options.namelist:
         parser.error("non-empty particle name or namelist required (use --name particlename or --namelist namelist)")
-    namelist = []
     if options.namelist:
         if not os.path.exists(options.namelist):
             parser.error("Namelist %s does not exist" % options.namelist)
         with open(options.namelist) as fp:
-            namelist = [line.strip() for line in fp.readlines()]
+            names = [line.strip() for line in fp.readlines()]
     else:
-        namelist = [options.name]
+        names = [options.name]
+    return parser, options, names
+
+
+def main(argv=None):
+    parser, options, namelist = _parse(argv)
 
     comm = None
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
