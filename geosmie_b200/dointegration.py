@@ -660,10 +660,17 @@ def fun(partID0, datatype, oppfx, oppclassic, elide=True, write=True, comm=None,
     return out
 
 
-def write_table(ncdfID, oppfx, out, oppclassic):
+def write_table(ncdfID, oppfx, out, oppclassic, hydrophobic_bin=False):
     """Write the arrays of `fun` with createNCDF's layout (new: (bin, wavelength, rh[, ang|p]); legacy:
-    (radius, rh, lambda[, ang]) and pback (nPol, radius, rh, lambda), dointegration.py:356-363, :1006-1031)."""
-    nc = createNCDF(ncdfID, oppfx, out['radius'], out['rh'], out['wavelength'], out['ang'], oppclassic)
+    (radius, rh, lambda[, ang]) and pback (nPol, radius, rh, lambda), dointegration.py:356-363, :1006-1031).
+    hydrophobic_bin=True applies hydrophobic.doConversion's rule in memory (a new first bin holding the RH-index-0
+    values at every RH, hydrophobic.py:38-113) instead of the reference's write / rename / re-read / re-write cycle."""
+    from . import hydrophobic
+    radius = list(out['radius'])
+    if hydrophobic_bin:
+        radius = [radius[0], radius[0]]
+    nc = createNCDF(ncdfID, oppfx, radius, out['rh'], out['wavelength'], out['ang'], oppclassic)
+    rname = 'radius' if oppclassic else 'bin'
     for key, a in out['vals'].items():
         kind = _kind_of(key)
         if oppclassic:
@@ -673,5 +680,7 @@ def write_table(ncdfID, oppfx, out, oppclassic):
                 a = a.transpose(3, 0, 2, 1)
             elif kind == "scal":
                 a = a.transpose(0, 2, 1)
+        if hydrophobic_bin:
+            a = hydrophobic._convert_var(key, a, tuple(nc.variables[key].dimensions), rname)
         nc.variables[key][:] = a
     nc.close()

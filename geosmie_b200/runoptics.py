@@ -5,10 +5,9 @@
     torchrun --nproc-per-node 8 -m geosmie_b200.runoptics --name geosparticles/ss.json     # cells sharded over 8 GPUs
 """
 import os
-import shutil
 from optparse import OptionParser
 
-from . import dointegration, hydrophobic
+from . import dointegration
 from . import particleparams as pp
 
 
@@ -67,14 +66,16 @@ def main(argv=None):
             fn = fn1
         params = pp.getParticleParams(fn, options.datatype)
         particlename = fn.split('/')[-1].replace(".json", "")
-        dointegration.fun(fn, options.datatype, options.dest, options.classic, elide=not options.dense, comm=comm)
+        # Species with "hydrophobic": true get a hydrophobic bin prepended (RH-index-0 values at all RH).  The reference
+        # writes the table, renames it, re-reads it in hydrophobic.doConversion and writes it again (runoptics.py:113-121);
+        # here the same rule is applied to the arrays in memory and the file is written once.
+        hp = bool(params.get("hydrophobic"))
+        out = dointegration.fun(fn, options.datatype, options.dest, options.classic, elide=not options.dense, comm=comm,
+                                write=not hp)
         opfn = "optics_%s.nomom.legacy.nc4" % particlename if options.classic else "optics_%s.nomom.nc4" % particlename
-        if rank == 0 and "hydrophobic" in params and params["hydrophobic"]:
-            fn2 = "%s.nohp" % opfn
-            shutil.move(os.path.join(options.dest, opfn), os.path.join(options.dest, fn2))
+        if rank == 0 and hp:
             print("Starting hydrophobic bin handling")
-            hydrophobic.doConversion(fn2, opfn, options.dest, options.classic)
-            os.remove(os.path.join(options.dest, fn2))
+            dointegration.write_table(particlename, options.dest, out, options.classic, hydrophobic_bin=True)
         print("Done, output file: %s" % opfn)
     if comm is not None:
         comm.close()
