@@ -75,6 +75,13 @@ MINI = {
                                               "fracs": [[0.7, 0.3], [0.4, 0.6]]}},
         "ri": {"format": "wsv", "path": ["ri-bc_mini.wsv", "ri-b2_mini.wsv"]}},
         {"ri-bc_mini.wsv": RI_BC, "ri-b2_mini.wsv": RI_B2}),
+    # sulfate with CARMA growth (rhDep type 'su', particleparams.py:101-108 -> carma_utils.grow_v75)
+    "sucarma_mini": ({
+        "rhop0": 1923.0, "rh": [0.0, 0.3, 0.8, 0.95],
+        "rhDep": {"type": "su", "params": {"temp": 220.0}},
+        "psd": {"type": "lognorm", "params": {"r0": [[0.08e-6]], "rmin0": [[0.01e-6]], "rmax0": [[0.5e-6]],
+                                              "sigma": [[1.6]], "numperdec": [30], "fracs": [[1.0]]}},
+        "ri": {"format": "wsv", "path": ["ri-su_mini.wsv"]}}, {"ri-su_mini.wsv": RI_SU}),
 }
 
 
@@ -91,6 +98,8 @@ def dump_dataset(store):
 def gen_fun():
     """Full dointegration.fun (+ hydrophobic.doConversion) tables for the mini configs, new and legacy layout."""
     for name, (cfg, files) in MINI.items():
+        if ONLY and name not in ONLY:
+            continue
         extra = {name + ".json": json.dumps(cfg)}
         extra.update(files)
         for classic in (False, True):
@@ -267,6 +276,18 @@ def gen_hostlogic():
     print("wrote hostlogic")
 
 
+def gen_carma():
+    """carma_utils.wtpct / dens / grow_v75 (carma_utils.py:136-314) on a sweep of (RH, dry radius, temperature)."""
+    import carma_utils as cu
+    rng = np.random.default_rng(4)
+    rh = np.concatenate([[1e-7, 0.01, 0.049, 0.05, 0.5, 0.85, 0.851, 0.99, 1.0], rng.uniform(0, 1, 60)])
+    rd = 10 ** rng.uniform(-8.5, -5.5, rh.size)
+    temp = np.concatenate([np.full(9, 220.0), rng.uniform(190, 260, 60)])
+    out = np.array([[cu.wtpct(a, temp=t), cu.dens(a, temp=t), float(cu.grow_v75(a, r, temp=t))] for a, r, t in zip(rh, rd, temp)])
+    np.savez_compressed(os.path.join(HERE, "carma_growth.npz"), rh=rh, rd=rd, temp=temp, out=out)
+    print("wrote carma_growth")
+
+
 def gen_bands():
     """bandaverage.doAverage / getBands (bandaverage.py:18-50, :73-124) on a synthetic spectrum."""
     BA = R.bandaverage
@@ -290,7 +311,12 @@ def gen_bands():
     print("wrote bands")
 
 
+ONLY = [a[4:] for a in sys.argv[1:] if a.startswith("fun:")]
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["single", "size_range", "cells", "hostlogic", "bands", "fun"]
+    if ONLY:
+        gen_fun()
+        sys.exit(0)
+    which = sys.argv[1:] or ["single", "size_range", "cells", "hostlogic", "bands", "carma", "fun"]
     for w in which:
         globals()["gen_" + w]()
