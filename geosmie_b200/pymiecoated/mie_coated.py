@@ -66,8 +66,18 @@ class MultipleMie(object):
     def preCalculatePT(self):
         self._ensure_table()
 
+    MAX_TABLE_ANGLES = 384      # angle capacity of the DMMA table path (2 halves x 192)
+
+    def _direct(self, mr, mi):
+        """More angles than the table path holds: one warp per particle, lanes over angles (k_s12_direct)."""
+        eps = complex(mr, mi) ** 2
+        x = np.asarray(self.xArr, dtype=float)
+        q, s12, _ = _lib.Handle.get().mie_eval(x, [np.sqrt(eps * 1.0)], [np.sqrt(eps / 1.0)], nmax_of(x),
+                                               u=np.asarray(self.costarr, dtype=float))
+        return q, s12
+
     def _ensure_table(self):
-        if self.yArr is not None:
+        if self.yArr is not None or len(self.costarr) > self.MAX_TABLE_ANGLES:
             return None
         if self._table is None:
             x = np.asarray(self.xArr, dtype=float)
@@ -84,10 +94,7 @@ class MultipleMie(object):
         x = np.asarray(self.xArr, dtype=float)
         cost = np.asarray(self.costarr, dtype=float)
         if self.yArr is None:
-            # single-layer sphere through the DMMA table path
-            t = self._ensure_table()
-            q, s12 = t.particles([np.sqrt(eps * mu)], [np.sqrt(eps / mu)], want_s12=True)
-            q, s12 = q[0], s12[0]
+            q, s12 = self.calculateS12SizeRangeArrays(mr, mi)
         else:
             # the reference calls an undefined coated_mie_coeff_numba here (mie_coated.py:80); this build evaluates the
             # coated sphere (core xArr, shell yArr; core index (mr, mi) is not enough for two materials, so the batch
@@ -106,7 +113,9 @@ class MultipleMie(object):
         """Extension: same evaluation, numpy arrays (q [nx][6], s12 [nx][nang][4]) instead of lists of tuples."""
         eps = complex(mr, mi) ** 2
         t = self._ensure_table()
-        q, s12 = t.particles([np.sqrt(eps * 1.0)], [np.sqrt(eps / 1.0)], want_s12=True)
+        if t is None:
+            return self._direct(mr, mi)
+        q, s12 = t.particles([np.sqrt(eps * 1.0)], [np.sqrt(eps / 1.0)], want_s12=True)     # DMMA table path
         return q[0], s12[0]
 
 
