@@ -15,7 +15,7 @@ from scipy.interpolate import interp1d
 
 from . import _lib, ncio
 from . import particleparams as pp
-from .pymiecoated.mie_coated import MultipleMie
+from .pymiecoated.mie_coated import MultipleMie  # noqa: F401  (re-exported like the reference module does)
 from .pymiecoated.mie_coeffs import nmax_of
 
 # key groups, same names and order as the reference (dointegration.py:16-24); the order of scalarkeys matters (:1156-1157)

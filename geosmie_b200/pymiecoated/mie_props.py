@@ -5,21 +5,16 @@ The functions that take a coefficient object re-evaluate particle -> (a_n, b_n) 
 """
 import numpy as np
 
-from .. import _lib
-
-
 def mie_props(coeffs, y):
     """The scattering properties (mie_props.py:72-75)."""
     q = coeffs._eval()[0][0]
     return {"qext": float(q[0]), "qsca": float(q[1]), "qabs": float(q[2]), "qb": float(q[3]), "asy": float(q[4]),
             "qratio": float(q[5])}
 
-
 def mie_S12(coeffs, u):
     """The amplitude scattering matrix (mie_props.py:108-110, :119-131)."""
     s = coeffs._eval(u=[u])[1][0, 0]
     return (complex(s[0], s[1]), complex(s[2], s[3]))
-
 
 def mie_S12_pt(coeffs, pin, tin):
     """S1,S2 from caller-supplied pre-multiplied pi_n/tau_n arrays (mie_props.py:112-113, :133-150).
@@ -27,7 +22,6 @@ def mie_S12_pt(coeffs, pin, tin):
     pin = np.asarray(pin, dtype=float)
     u = float(pin[1] / pin[0] * 1.5 / (5.0 / 6.0) / 3.0) if len(pin) > 1 else float(np.asarray(tin)[0] / 1.5)
     return mie_S12(coeffs, u)
-
 
 def mie_pt(u, nmax):
     """pi_n, tau_n pre-multiplied by (2n+1)/(n(n+1)) (mie_props.py:194-195, :217-231).  Host-side helper: these
@@ -44,6 +38,5 @@ def mie_pt(u, nmax):
     k = np.arange(1, max(nmax, 2) + 1, dtype=float)
     n2 = (2 * k + 1) / (k * (k + 1))
     return (p * n2)[:nmax], (t * n2)[:nmax]
-
 
 mie_ptnumba = mie_pt

@@ -8,7 +8,6 @@
                               bins of ss.json (the whole SS table takes 6-15 h on one core).
     python tests/golden/make_golden_full.py [su] [bc] [ss]
 """
-import json
 import os
 import sys
 

@@ -5,7 +5,6 @@ import socket
 import subprocess
 import sys
 
-import numpy as np
 
 from geosmie_b200 import dist
 
