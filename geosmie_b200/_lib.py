@@ -11,6 +11,7 @@ LIB_PATH = os.environ.get("GEOSMIE_LIB", os.path.join(_HERE, "libgeosmie_b200.so
 GM_NSCAL = 11
 S_W, S_X2W, S_X3W, S_X4W, S_QEXT, S_QSCA, S_QABS, S_QB, S_G, S_CSCA, S_CEXT = range(11)
 F_ELIDE_ZERO_WEIGHT = 1
+F_NO_GRAM = 2
 PSD_LOGNORM, PSD_SS, PSD_DU, PSD_NPAR = 1, 2, 3, 4
 
 _lib = None
@@ -49,6 +50,7 @@ SIGNATURES = {
     "gm_table_last_stats": (C.c_int, [vp, vp]),
     "gm_table_set_timing": (C.c_int, [vp, C.c_int]),
     "gm_table_last_kernel_ms": (C.c_int, [vp, c_dp, c_dp, c_dp]),
+    "gm_table_last_kernel_ms_ex": (C.c_int, [vp, vp, vp]),
     "gm_gsf_expand": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int]),
     "gm_gsf_expand_dev": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int]),
     "gm_gsf_expand_phase4_dev": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int]),
@@ -194,6 +196,11 @@ class Table:
         self.t = t
         self.nx = self.x.size
         self.nang = self.cost.size
+        # GM_F_NO_GRAM: force the per-angle contraction for every particle group (ablation / cross-check of the Gram path)
+        self.no_gram = os.environ.get("GEOSMIE_NO_GRAM", "0") not in ("", "0")
+
+    def _flags(self, elide):
+        return (F_ELIDE_ZERO_WEIGHT if elide else 0) | (F_NO_GRAM if self.no_gram else 0)
 
     def close(self):
         if getattr(self, "t", None):
@@ -224,7 +231,7 @@ class Table:
             assert ws.shape == (ntask, nmode, self.nx)
         scal = np.empty((ntask, nmode, GM_NSCAL))
         phase = np.empty((ntask, 4, self.nang))
-        check(self.lib.gm_table_run(self.t, ntask, ptr(mz), ptr(mrel), nmode, ptr(wp), ptr(ws), F_ELIDE_ZERO_WEIGHT if elide else 0,
+        check(self.lib.gm_table_run(self.t, ntask, ptr(mz), ptr(mrel), nmode, ptr(wp), ptr(ws), self._flags(elide),
                                     ptr(scal), ptr(phase)))
         return scal, phase
 
@@ -242,7 +249,7 @@ class Table:
         scal = np.empty((ntask, nmode, GM_NSCAL))
         phase = np.empty((ntask, 4, self.nang))
         check(self.lib.gm_table_run_coated(self.t, ntask, ptr(m1), ptr(m2), ptr(ratio), nmode, ptr(wp), ptr(ws),
-                                           F_ELIDE_ZERO_WEIGHT if elide else 0, ptr(scal), ptr(phase)))
+                                           self._flags(elide), ptr(scal), ptr(phase)))
         return scal, phase
 
     def set_gsf(self, ang_deg, ng=129, quantize10=False, coef_out=None, cnorm_out=None):
@@ -272,7 +279,7 @@ class Table:
         frac = f64(np.broadcast_to(frac, (ntask, nmode)))
         scal, phase = out if out is not None else (np.empty((ntask, nmode, GM_NSCAL)), np.empty((ntask, 4, self.nang)))
         check(self.lib.gm_table_run_psd(self.t, ntask, ptr(mz), ptr(mrel), nmode, int(kind), ptr(params), ptr(frac),
-                                        F_ELIDE_ZERO_WEIGHT if elide else 0, ptr(scal), ptr(phase)))
+                                        self._flags(elide), ptr(scal), ptr(phase)))
         self._last_psd_shape = (ntask, nmode)
         return scal, phase
 
@@ -284,7 +291,7 @@ class Table:
 
     def run_into(self, ntask, mz, mrel, w_phase, scal_out, phase_out, elide=False):
         """Host-buffer call writing into caller-provided (ideally pinned) numpy arrays; single-mode weights."""
-        check(self.lib.gm_table_run(self.t, ntask, ptr(mz), ptr(mrel), 1, ptr(w_phase), None, F_ELIDE_ZERO_WEIGHT if elide else 0,
+        check(self.lib.gm_table_run(self.t, ntask, ptr(mz), ptr(mrel), 1, ptr(w_phase), None, self._flags(elide),
                                     ptr(scal_out), ptr(phase_out)))
 
     def device_outputs(self):
@@ -295,7 +302,7 @@ class Table:
     def run_dev(self, ntask, mz_ptr, mrel_ptr, nmode, wphase_ptr, wscal_ptr, out_scal_ptr, out_phase_ptr, elide=False):
         """Device-pointer call (asynchronous on the handle's stream); pointers are integers (tensor.data_ptr())."""
         check(self.lib.gm_table_run_dev(self.t, ntask, vp(mz_ptr), vp(mrel_ptr), nmode, vp(wphase_ptr),
-                                        vp(wscal_ptr) if wscal_ptr else None, F_ELIDE_ZERO_WEIGHT if elide else 0,
+                                        vp(wscal_ptr) if wscal_ptr else None, self._flags(elide),
                                         vp(out_scal_ptr), vp(out_phase_ptr)))
 
     def particles(self, mz, mrel, want_s12=True):
@@ -318,4 +325,8 @@ class Table:
     def last_kernel_ms(self):
         a, b, c = C.c_double(), C.c_double(), C.c_double()
         check(self.lib.gm_table_last_kernel_ms(self.t, C.byref(a), C.byref(b), C.byref(c)))
-        return {"coeff": a.value, "contract": b.value, "finalize": c.value}
+        ms, n = np.zeros(5), np.zeros(5, dtype=np.int32)
+        check(self.lib.gm_table_last_kernel_ms_ex(self.t, ptr(ms), ptr(n)))
+        return {"coeff": a.value, "contract": b.value, "finalize": c.value,
+                "k_contract": ms[1], "k_gram": ms[3], "k_gram_eval": ms[4],
+                "launches": dict(zip(("k_coeff", "k_contract", "k_finalize", "k_gram", "k_gram_eval"), n.tolist()))}

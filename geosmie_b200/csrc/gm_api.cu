@@ -9,6 +9,7 @@
 #include "gm_mie_kernels.cuh"
 #include "gm_coated.cuh"
 #include "gm_psd.cuh"
+#include "gm_gram.cuh"
 
 // ------------------------------------------------------------------------------------------------ errors / lifetime
 static thread_local char g_err[512] = "";
@@ -42,6 +43,8 @@ extern "C" int gm_init(int device, gm_handle_t* out) {
   const int smem = GM_CONTRACT_SMEM;
   GM_CUDA_TRY(cudaFuncSetAttribute(k_contract<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   GM_CUDA_TRY(cudaFuncSetAttribute(k_contract<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  GM_CUDA_TRY(cudaFuncSetAttribute(k_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_GRAM_SMEM));
+  GM_CUDA_TRY(cudaFuncSetAttribute(k_gram_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_GRAM_EVAL_SMEM_MAX));
   *out = h;
   return GM_OK;
 }
@@ -85,6 +88,40 @@ struct Groups {
   std::vector<int> gk4, grow;    // DMMA k4 steps and first coefficient row of group g
   long long bessel_len = 0;      // doubles per Bessel table
   long long task_rows = 0;       // coefficient rows per task
+  // Gram path (gm_gram.cuh): groups with max nmax <= 64, listed class by class (class = number of 8-row tiles, 5 -> 6, 7 -> 8)
+  std::vector<unsigned char> gskip;   // 1 = Gram group
+  std::vector<int> glist;             // Gram groups ordered by class, ascending group index inside a class
+  int cls_begin[GM_GRAM_MAX_TG + 2] = {0};   // glist range of class c: [cls_begin[c], cls_begin[c + 1])
+  int gram_nmax = 0;                  // largest nmax among Gram groups
+  int gram_tgmax = 0;                 // largest class present
+  int ndirect = 0;                    // groups left to the per-angle contraction
+  static int gram_class(int gm) {
+    int tg = (gm + 7) / 8;
+    if (tg == 5) tg = 6;
+    if (tg == 7) tg = 8;
+    return tg;
+  }
+  void build_gram(const int32_t* nmax) {
+    gskip.assign(ngroup, 0);
+    glist.clear();
+    gram_nmax = gram_tgmax = 0;
+    std::vector<int> gm(ngroup, 0);
+    for (int g = 0; g < ngroup; ++g)
+      for (int i = g * GM_GROUP; i < std::min(nx, (g + 1) * GM_GROUP); ++i) gm[g] = std::max(gm[g], (int)nmax[i]);
+    for (int c = 1; c <= GM_GRAM_MAX_TG; ++c) {
+      cls_begin[c] = (int)glist.size();
+      for (int g = 0; g < ngroup; ++g)
+        if (gm[g] <= 8 * GM_GRAM_MAX_TG && gram_class(gm[g]) == c) {
+          glist.push_back(g);
+          gskip[g] = 1;
+          gram_nmax = std::max(gram_nmax, gm[g]);
+          gram_tgmax = std::max(gram_tgmax, c);
+        }
+    }
+    cls_begin[GM_GRAM_MAX_TG + 1] = (int)glist.size();
+    cls_begin[0] = 0;
+    ndirect = ngroup - (int)glist.size();
+  }
   void build(int n, const int32_t* nmax) {
     nx = n;
     ngroup = (n + GM_GROUP - 1) / GM_GROUP;
@@ -104,6 +141,7 @@ struct Groups {
       grow[g] = (int)task_rows;
       task_rows += (long long)gk4[g] * GM_KSTEP;
     }
+    build_gram(nmax);
   }
 };
 
@@ -272,6 +310,7 @@ struct gm_table_s {
   std::vector<double> hx;
   std::vector<int32_t> hnmax;
   DevBuf T, cost, dr, psd_par, psd_frac;
+  DevBuf g_list, g_skip, g_zeros, g_desc, g_items, g_hpart, g_hsum;   // Gram path (gm_gram.cuh)
   DevBuf c_ab, c_scratch, c_soff, c_aboff, c_ratio;   // coated-sphere table path
   // fused GSF stage (gm_table_set_gsf): moments of every finished batch are expanded and downloaded behind the kernels
   std::vector<double> gsf_ang;
@@ -289,10 +328,10 @@ struct gm_table_s {
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // host-buffer calls: copies pipelined against the kernels
   std::vector<cudaEvent_t> io_events;
   std::vector<cudaEvent_t> evpool;   // pairs of events recorded around every launch of the last run (timing mode)
-  std::vector<int> evkind;           // 0 coeff, 1 contract, 2 finalize
+  std::vector<int> evkind;           // 0 coeff, 1 contract, 2 finalize, 3 gram, 4 gram_eval
   size_t evused = 0;
-  double ms_coeff = 0, ms_contract = 0, ms_finalize = 0;
-  int n_coeff = 0, n_contract = 0, n_finalize = 0;
+  double ms_coeff = 0, ms_contract = 0, ms_finalize = 0, ms_gram = 0, ms_gram_eval = 0;
+  int n_coeff = 0, n_contract = 0, n_finalize = 0, n_gram = 0, n_gram_eval = 0;
 };
 
 extern "C" int gm_table_create(gm_handle_t h, int nx, const double* x, const int32_t* nmax, int nang, const double* cos_theta,
@@ -319,6 +358,16 @@ extern "C" int gm_table_create(gm_handle_t h, int nx, const double* x, const int
   }
   GM_CUDA_TRY(cudaMemcpyAsync(t->cost.p, cos_theta, sizeof(double) * nang, cudaMemcpyHostToDevice, st));
   GM_CUDA_TRY(cudaMemsetAsync(t->T.p, 0, sizeof(double) * GM_NHALF * (size_t)t->nrows * GM_TROW, st));
+  if (!t->G.glist.empty()) {
+    if ((rc = t->g_list.ensure(sizeof(int) * t->G.glist.size())) || (rc = t->g_skip.ensure(t->G.ngroup)) ||
+        (rc = t->g_zeros.ensure(sizeof(double) * GM_GRAM_ZERO_DBL))) {
+      delete t;
+      return rc;
+    }
+    GM_CUDA_TRY(cudaMemcpyAsync(t->g_list.p, t->G.glist.data(), sizeof(int) * t->G.glist.size(), cudaMemcpyHostToDevice, st));
+    GM_CUDA_TRY(cudaMemcpyAsync(t->g_skip.p, t->G.gskip.data(), t->G.ngroup, cudaMemcpyHostToDevice, st));
+    GM_CUDA_TRY(cudaMemsetAsync(t->g_zeros.p, 0, sizeof(double) * GM_GRAM_ZERO_DBL, st));
+  }
   k_bessel<<<(nx + 127) / 128, 128, 0, st>>>(nx, t->D.x.as<double>(), t->D.nmax.as<int>(), t->D.gboff.as<long long>(),
                                              t->D.psi.as<double>(), t->D.chi.as<double>());
   GM_LAUNCH_CHECK(h);
@@ -333,7 +382,7 @@ extern "C" int gm_table_destroy(gm_table_t t) {
   if (!t) return GM_OK;
   cudaSetDevice(t->h->device);
   t->D.release();
-  for (DevBuf* b : {&t->gsf_coef, &t->gsf_cnorm, &t->c_ab, &t->c_scratch, &t->c_soff, &t->c_aboff, &t->c_ratio, &t->dr, &t->psd_par, &t->psd_frac, &t->T, &t->cost, &t->coef, &t->gact, &t->scal_part, &t->part, &t->chunk_start, &t->mz, &t->mrel, &t->wphase,
+  for (DevBuf* b : {&t->g_hsum, &t->g_list, &t->g_skip, &t->g_zeros, &t->g_desc, &t->g_items, &t->g_hpart, &t->gsf_coef, &t->gsf_cnorm, &t->c_ab, &t->c_scratch, &t->c_soff, &t->c_aboff, &t->c_ratio, &t->dr, &t->psd_par, &t->psd_frac, &t->T, &t->cost, &t->coef, &t->gact, &t->scal_part, &t->part, &t->chunk_start, &t->mz, &t->mrel, &t->wphase,
                     &t->wscal, &t->out_scal, &t->out_phase, &t->stats, &t->q, &t->s12})
     b->release();
   for (auto& e : t->evpool) cudaEventDestroy(e);
@@ -396,19 +445,34 @@ extern "C" int gm_table_last_kernel_ms(gm_table_t t, double* a, double* b, doubl
   if (t->timing && t->evused) {
     GM_CUDA_TRY(cudaSetDevice(t->h->device));
     GM_CUDA_TRY(cudaStreamSynchronize(t->h->stream));
-    t->ms_coeff = t->ms_contract = t->ms_finalize = 0;
-    t->n_coeff = t->n_contract = t->n_finalize = 0;
+    t->ms_coeff = t->ms_contract = t->ms_finalize = t->ms_gram = t->ms_gram_eval = 0;
+    t->n_coeff = t->n_contract = t->n_finalize = t->n_gram = t->n_gram_eval = 0;
     for (size_t i = 0; i + 1 < t->evused; i += 2) {
       float ms = 0;
       GM_CUDA_TRY(cudaEventElapsedTime(&ms, t->evpool[i], t->evpool[i + 1]));
       if (t->evkind[i] == 0) { t->ms_coeff += ms; t->n_coeff++; }
       if (t->evkind[i] == 1) { t->ms_contract += ms; t->n_contract++; }
       if (t->evkind[i] == 2) { t->ms_finalize += ms; t->n_finalize++; }
+      if (t->evkind[i] == 3) { t->ms_gram += ms; t->n_gram++; }
+      if (t->evkind[i] == 4) { t->ms_gram_eval += ms; t->n_gram_eval++; }
     }
   }
   if (a) *a = t->ms_coeff;
-  if (b) *b = t->ms_contract;
+  if (b) *b = t->ms_contract + t->ms_gram + t->ms_gram_eval;   // the whole angular stage
   if (c) *c = t->ms_finalize;
+  return GM_OK;
+}
+
+// per-kernel split of the last run: ms[0..4] = k_coeff, k_contract, k_finalize, k_gram, k_gram_eval; n[0..4] = launches of each
+extern "C" int gm_table_last_kernel_ms_ex(gm_table_t t, double ms[5], int32_t n[5]) {
+  int rc = gm_table_last_kernel_ms(t, nullptr, nullptr, nullptr);
+  if (rc) return rc;
+  if (ms) {
+    ms[0] = t->ms_coeff; ms[1] = t->ms_contract; ms[2] = t->ms_finalize; ms[3] = t->ms_gram; ms[4] = t->ms_gram_eval;
+  }
+  if (n) {
+    n[0] = t->n_coeff; n[1] = t->n_contract; n[2] = t->n_finalize; n[3] = t->n_gram; n[4] = t->n_gram_eval;
+  }
   return GM_OK;
 }
 
@@ -456,27 +520,100 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
       return rc;
   }
   if (hio && ntask >= 256) tb = std::min(tb, (ntask + 3) / 4);   // at least 4 batches so that copies overlap compute
-  // chunks: enough CTAs to fill the machine ~8x over, cost-balanced by k4 steps
-  const int want_items = GM_WANT_ITEMS_CFG * h->sm_count;   // equal-cost CTAs per SM: bounds the last-wave tail
-  int nchunk = (want_items + 2 * tb - 1) / (2 * tb);
-  nchunk = std::max(nchunk, (G.ngroup + GM_MAX_CHUNK_GROUPS / 2 - 1) / (GM_MAX_CHUNK_GROUPS / 2));   // chunk metadata must fit in smem
-  nchunk = std::max(1, std::min(nchunk, G.ngroup));
-  std::vector<int> cstart(nchunk + 1, 0);
-  {
+  const bool use_gram = !per_particle && !(flags & GM_F_NO_GRAM) && !G.glist.empty();
+  const int ndirect = use_gram ? G.ndirect : G.ngroup;
+  // chunks of the per-angle contraction: enough CTAs to fill the machine ~8x over, cost-balanced by the k4 steps of the
+  // groups it handles (groups taken by the Gram path cost nothing here); a chunk never holds more groups than the smem metadata
+  std::vector<int> cstart(1, 0);
+  int nchunk = 0;
+  if (ndirect > 0) {
+    const int want_items = GM_WANT_ITEMS_CFG * h->sm_count;   // equal-cost CTAs per SM: bounds the last-wave tail
+    int want = (want_items + 2 * tb - 1) / (2 * tb);
+    want = std::max(1, std::min(want, ndirect));
     long long tot = 0;
-    for (int g = 0; g < G.ngroup; ++g) tot += G.gk4[g];
+    for (int g = 0; g < G.ngroup; ++g) tot += (use_gram && G.gskip[g]) ? 0 : G.gk4[g];
     long long acc = 0;
-    int c = 1;
-    for (int g = 0; g < G.ngroup && c < nchunk; ++g) {
-      acc += G.gk4[g];
-      if (acc * nchunk >= tot * c) cstart[c++] = g + 1;
+    int made = 1;
+    for (int g = 0; g + 1 < G.ngroup; ++g) {
+      acc += (use_gram && G.gskip[g]) ? 0 : G.gk4[g];
+      const bool cut = made < want && acc * want >= tot * made;
+      if (cut || g + 1 - cstart.back() >= GM_MAX_CHUNK_GROUPS) {
+        cstart.push_back(g + 1);
+        if (cut) ++made;
+      }
     }
-    for (; c < nchunk; ++c) cstart[c] = G.ngroup;
-    cstart[nchunk] = G.ngroup;
+    cstart.push_back(G.ngroup);
+    nchunk = (int)cstart.size() - 1;
+  }
+  const int nchunk_total = nchunk + (use_gram ? 1 : 0);
+  const int nbatch = (ntask + tb - 1) / tb;
+  // Gram plan(s): descriptors (class, group range, partial slot) and CTA work items (descriptor, task range) per batch size
+  struct GramPlan {
+    int nt = 0, desc0 = 0, ndesc = 0, item0 = 0, nitem = 0;
+    long long hstride = 0;
+  };
+  std::vector<GramPlan> plans;
+  std::vector<GramDesc> all_desc;
+  std::vector<GramItem> all_items;
+  if (use_gram) {
+    for (int b = 0; b < nbatch; ++b) {
+      const int nt = std::min(tb, ntask - b * tb);
+      if (!plans.empty() && plans.back().nt == nt) continue;
+      GramPlan P;
+      P.nt = nt;
+      P.desc0 = (int)all_desc.size();
+      P.item0 = (int)all_items.size();
+      double ccost[GM_GRAM_MAX_TG + 1] = {0};
+      double total = 0;
+      for (int c = 1; c <= GM_GRAM_MAX_TG; ++c) {
+        const int nc = G.cls_begin[c + 1] - G.cls_begin[c];
+        ccost[c] = (double)nc * (64.0 * c * c + 48.0);   // DMMA issue slots per task (+ ring handling per group)
+        total += ccost[c] * nt;
+      }
+      const double target = std::max(total / (h->sm_count * 6.0), 12000.0);
+      std::vector<std::pair<double, GramItem>> items;
+      for (int c = 1; c <= GM_GRAM_MAX_TG; ++c) {
+        const int nc = G.cls_begin[c + 1] - G.cls_begin[c];
+        if (nc == 0) continue;
+        const int nteam = c == 1 ? 12 : c == 2 ? 6 : c <= 4 ? 3 : 1;   // GramCfg<c>::NTEAM
+        int nsplit = 1, tpc = 1;
+        if (ccost[c] > 1.5 * target) nsplit = std::min(nc, (int)std::lround(ccost[c] / target));
+        else tpc = std::max(1, std::min(nt, (int)(target / ccost[c])));
+        tpc = (nt + ((nt + tpc - 1) / tpc) - 1) / ((nt + tpc - 1) / tpc);   // even task ranges
+        for (int k = 0; k < nsplit; ++k) {
+          GramDesc d;
+          d.tg = c;
+          d.nteam = nteam;
+          d.gbegin = G.cls_begin[c] + (int)((long long)nc * k / nsplit);
+          d.gend = G.cls_begin[c] + (int)((long long)nc * (k + 1) / nsplit);
+          d.hoff = P.hstride;
+          P.hstride += (long long)nteam * 4 * 64 * c * c;
+          const int di = (int)all_desc.size() - P.desc0;
+          all_desc.push_back(d);
+          for (int t0 = 0; t0 < nt; t0 += tpc) {
+            GramItem it = {di, t0, std::min(nt, t0 + tpc)};
+            items.push_back({ccost[c] / nsplit * (it.t1 - it.t0), it});
+          }
+        }
+      }
+      std::stable_sort(items.begin(), items.end(), [](const auto& a, const auto& b) { return a.first > b.first; });
+      for (auto& e : items) all_items.push_back(e.second);
+      P.ndesc = (int)all_desc.size() - P.desc0;
+      P.nitem = (int)all_items.size() - P.item0;
+      plans.push_back(P);
+    }
+    long long hmax = 0;
+    for (auto& P : plans) hmax = std::max(hmax, P.hstride * P.nt);
+    if ((rc = t->g_desc.ensure(sizeof(GramDesc) * all_desc.size())) || (rc = t->g_items.ensure(sizeof(GramItem) * all_items.size())) ||
+        (rc = t->g_hpart.ensure(sizeof(double) * (size_t)hmax)) ||
+        (rc = t->g_hsum.ensure(sizeof(double) * (size_t)tb * 4 * 64 * G.gram_tgmax * G.gram_tgmax)))
+      return rc;
+    GM_CUDA_TRY(cudaMemcpyAsync(t->g_desc.p, all_desc.data(), sizeof(GramDesc) * all_desc.size(), cudaMemcpyHostToDevice, st));
+    GM_CUDA_TRY(cudaMemcpyAsync(t->g_items.p, all_items.data(), sizeof(GramItem) * all_items.size(), cudaMemcpyHostToDevice, st));
   }
   if ((rc = t->coef.ensure(per_task_bytes * tb)) || (rc = t->gact.ensure((size_t)tb * G.ngroup)) ||
       (rc = t->scal_part.ensure(sizeof(double) * (size_t)tb * nmode * G.ngroup * GM_NSCAL)) ||
-      (rc = t->part.ensure(sizeof(double) * (size_t)tb * nchunk * 4 * GM_NANG_PAD)) ||
+      (rc = t->part.ensure(sizeof(double) * (size_t)tb * nchunk_total * 4 * GM_NANG_PAD)) ||
       (rc = t->chunk_start.ensure(sizeof(int) * (nchunk + 1))) || (rc = t->stats.ensure(sizeof(unsigned long long) * 8)))
     return rc;
   if (t->gsf_ng > 0 && !per_particle) {
@@ -489,7 +626,6 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
     GM_REQUIRE(cstart[c + 1] - cstart[c] <= GM_MAX_CHUNK_GROUPS, "chunk has more particle groups than the smem metadata holds");
   const int64_t launches0 = h->launches;
   t->evused = 0;
-  const int nbatch = (ntask + tb - 1) / tb;
   if (hio) {
     if (!t->h2d_stream) {
       GM_CUDA_TRY(cudaStreamCreateWithFlags(&t->h2d_stream, cudaStreamNonBlocking));
@@ -575,21 +711,78 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
     C.grow = t->D.grow.as<int>();
     C.gk4 = t->D.gk4.as<int>();
     C.gact = t->gact.as<unsigned char>();
+    C.gskip = use_gram ? t->g_skip.as<unsigned char>() : nullptr;
     C.chunk_start = t->chunk_start.as<int>();
     C.part = t->part.as<double>();
+    C.nchunk_total = nchunk_total;
     C.nx = G.nx;
     C.nang = t->nang;
     C.s12 = d_s12 ? d_s12 + (size_t)t0 * G.nx * t->nang * 4 : nullptr;
-    if ((rc = ev_mark(t, 1))) return rc;
-    if (per_particle)
-      k_contract<true><<<nt * 2 * nchunk, GM_CONTRACT_THREADS, smem, st>>>(C);
-    else
-      k_contract<false><<<nt * 2 * nchunk, GM_CONTRACT_THREADS, smem, st>>>(C);
-    GM_LAUNCH_CHECK(h);
-    if ((rc = ev_mark(t, 1))) return rc;
+    if (nchunk > 0) {
+      if ((rc = ev_mark(t, 1))) return rc;
+      if (per_particle)
+        k_contract<true><<<nt * 2 * nchunk, GM_CONTRACT_THREADS, smem, st>>>(C);
+      else
+        k_contract<false><<<nt * 2 * nchunk, GM_CONTRACT_THREADS, smem, st>>>(C);
+      GM_LAUNCH_CHECK(h);
+      if ((rc = ev_mark(t, 1))) return rc;
+    }
+    if (use_gram) {
+      const GramPlan* P = nullptr;
+      for (auto& q : plans)
+        if (q.nt == nt) P = &q;
+      GramArgs GA;
+      memset(&GA, 0, sizeof(GA));
+      GA.ngroup = G.ngroup;
+      GA.items = t->g_items.as<GramItem>() + P->item0;
+      GA.desc = t->g_desc.as<GramDesc>() + P->desc0;
+      GA.glist = t->g_list.as<int>();
+      GA.grow = t->D.grow.as<int>();
+      GA.gk4 = t->D.gk4.as<int>();
+      GA.gact = t->gact.as<unsigned char>();
+      GA.coef = t->coef.as<double>();
+      GA.task_stride = task_stride;
+      GA.zeros = t->g_zeros.as<double>();
+      GA.hpart = t->g_hpart.as<double>();
+      GA.hstride = P->hstride;
+      if ((rc = ev_mark(t, 3))) return rc;
+      k_gram<<<P->nitem, GM_GRAM_THREADS, GM_GRAM_SMEM, st>>>(GA);
+      GM_LAUNCH_CHECK(h);
+      if ((rc = ev_mark(t, 3))) return rc;
+      const int N = 8 * G.gram_tgmax;
+      GramSumArgs SA;
+      memset(&SA, 0, sizeof(SA));
+      SA.ndesc = P->ndesc;
+      SA.desc = GA.desc;
+      SA.hpart = GA.hpart;
+      SA.hstride = P->hstride;
+      SA.N = N;
+      SA.hsum = t->g_hsum.as<double>();
+      GramEvalArgs EA;
+      memset(&EA, 0, sizeof(EA));
+      EA.ntask = nt;
+      EA.tasks_per_cta = std::max(1, (nt + (2 * h->sm_count / 4) - 1) / (2 * h->sm_count / 4));
+      EA.hsum = SA.hsum;
+      EA.N = N;
+      EA.ntile = std::min((G.gram_nmax + 7) / 8, G.gram_tgmax);
+      EA.nk4 = std::min((G.gram_nmax + 3) / 4, 2 * G.gram_tgmax);
+      const int hbytes = 4 * N * (N + 4) * 8;
+      EA.nbuf = 2 * hbytes <= GM_GRAM_EVAL_SMEM_MAX ? 2 : 1;
+      EA.T = t->T.as<double>();
+      EA.nrows = t->nrows;
+      EA.part = t->part.as<double>();
+      EA.nchunk = nchunk_total;
+      EA.chunk = nchunk;
+      if ((rc = ev_mark(t, 4))) return rc;
+      k_gram_sum<<<dim3((2 * N * N + 255) / 256, nt), 256, 0, st>>>(SA);
+      GM_LAUNCH_CHECK(h);
+      k_gram_eval<<<dim3(4, (nt + EA.tasks_per_cta - 1) / EA.tasks_per_cta), GM_GRAM_EVAL_THREADS, EA.nbuf * hbytes, st>>>(EA);
+      GM_LAUNCH_CHECK(h);
+      if ((rc = ev_mark(t, 4))) return rc;
+    }
     if (!per_particle) {
       if ((rc = ev_mark(t, 2))) return rc;
-      k_finalize<<<nt, GM_NANG_PAD, 0, st>>>(nchunk, G.ngroup, nmode, t->nang, t->part.as<double>(), t->scal_part.as<double>(),
+      k_finalize<<<nt, GM_NANG_PAD, 0, st>>>(nchunk_total, G.ngroup, nmode, t->nang, t->part.as<double>(), t->scal_part.as<double>(),
                                              d_out_phase + (size_t)t0 * 4 * t->nang, d_out_scal + (size_t)t0 * nmode * GM_NSCAL);
       GM_LAUNCH_CHECK(h);
       if ((rc = ev_mark(t, 2))) return rc;

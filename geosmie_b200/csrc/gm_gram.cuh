@@ -1,0 +1,428 @@
+// gm_gram.cuh -- Gram-matrix form of the angular contraction + size-distribution reduction (sm_100a, FP64 DMMA).
+//
+// What it replaces: the same reference code as k_contract (mie_S12_backend_pt, mie_props.py:133-150; calculateScatVals,
+// dointegration.py:1044-1050; the phase part of integratePSD, :1164-1166), for particle groups with nmax <= 64.
+//
+// Idea.  With S+(u) = sum_n c+_n p_n(u), S-(u) = sum_n c-_n q_n(u) (see k_contract) the four weighted sums a table cell needs,
+//     A(u) = sum_p |S+|^2,  B(u) = sum_p |S-|^2,  Cr(u) + i Ci(u) = sum_p S+ conj(S-),
+// are quadratic forms in the angle functions:
+//     A = p^T H1 p,  B = q^T H2 q,  Cr = p^T H3 q,  Ci = p^T H4 q,
+//     H1 = X+ X+^T, H2 = X- X-^T, H3 = X+ X-^T, H4 = X~+ X-^T            (N x N, N = max nmax)
+// where row n of X+ (X-) holds (Re, Im) of c+_n (c-_n) of every particle and X~+ is X+ with (re, im) -> (im, -re).
+// The reduction over particles becomes the K dimension of a small GEMM (cost ~ 8 N^2 FMA per particle instead of
+// (4 N + 8) N_ang), the angle grid enters only once per cell (k_gram_eval).  For optics_SU (mean nmax 7.4, 371 angles) this
+// is ~9x less FP64 work than the per-angle contraction; numerically the two forms agree to ~1e-14 of max P11.
+//
+//   k_gram       CTA = (class of particle groups, range of tasks).  Groups are classed by tg = ceil(max nmax / 8) (number of
+//                8-row DMMA tiles); a class fixes how the 4 tg^2 accumulator tiles are split over `S` warps (a team) and how
+//                many teams (12 / S) work on different groups at the same time.  One TMA producer warp streams the
+//                coefficient rows of each group (contiguous in the stream written by k_coeff) into a shared-memory ring,
+//                zero-filling the slot up to 8 tg rows from a zero page; end-of-task markers travel through the same ring, so
+//                a CTA runs through several tasks without any CTA-wide barrier.
+//   k_gram_eval  CTA = task: sums the partial H (fixed order: deterministic), D = L^T H on DMMA, out = rowsum(D .* R).
+#pragma once
+#include "gm_mie_kernels.cuh"
+
+constexpr int GM_GRAM_MAX_TG = 8;                                    // groups with max nmax <= 64 take the Gram path
+constexpr int GM_GRAM_THREADS = (GM_CONTRACT_WARPS + 1) * 32;        // 12 consumer warps + 1 producer warp
+constexpr int GM_GRAM_MAX_SLOTS = 24;
+constexpr int GM_GRAM_RING_DBL = GM_GRAM_MAX_SLOTS * 8 * GM_SB;      // 202 752 B
+constexpr int GM_GRAM_SMEM = GM_GRAM_RING_DBL * 8 + 2 * GM_GRAM_MAX_SLOTS * 8 + GM_GRAM_MAX_SLOTS * 4;
+constexpr int GM_GRAM_ZERO_DBL = 8 * GM_GRAM_MAX_TG * GM_SB;         // zero page (doubles)
+
+struct GramDesc {
+  int tg;          // template class: 1, 2, 3, 4, 6 or 8 tiles
+  int nteam;       // teams writing separate partials
+  int gbegin, gend;  // range in glist
+  long long hoff;  // offset (doubles) of this descriptor's partials inside a task's partial-H block
+};
+struct GramItem {
+  int desc, t0, t1;
+};
+
+struct GramArgs {
+  int ngroup;
+  const GramItem* items;
+  const GramDesc* desc;
+  const int* glist;
+  const int* grow;
+  const int* gk4;
+  const unsigned char* gact;   // [ntask][ngroup]
+  const double* coef;
+  long long task_stride;
+  const double* zeros;
+  double* hpart;               // [ntask][hstride]
+  long long hstride;
+};
+
+template <int TG>
+struct GramCfg {
+  static constexpr int S = TG == 1 ? 1 : TG == 2 ? 2 : TG <= 4 ? 4 : 12;   // warps per team
+  static constexpr int NTEAM = GM_CONTRACT_WARPS / S;
+  static constexpr int DEPTH = TG <= 4 ? 2 : TG == 6 ? 4 : 3;              // ring slots per team
+  static constexpr int R = NTEAM * DEPTH;
+  static constexpr int SLOT_DBL = 8 * TG * GM_SB;
+  static constexpr int CW = (TG + 2) / 3;                                   // column tiles per warp when S == 12
+  static constexpr int NJOB = S == 1 ? 4 : S == 2 ? 2 : 1;
+  static constexpr int NI = TG;
+  static constexpr int NJ = S == 12 ? CW : TG;
+  static_assert(R <= GM_GRAM_MAX_SLOTS && R * SLOT_DBL <= GM_GRAM_RING_DBL, "ring does not fit");
+};
+
+constexpr int GRAM_TAG_DATA = 0, GRAM_TAG_END = 1;
+
+template <int TG>
+__device__ __forceinline__ void gram_cta(const GramArgs& A, const GramItem it, const GramDesc d, double* ring, uint64_t* full,
+                                         uint64_t* empty, volatile int* tags) {
+  using C = GramCfg<TG>;
+  constexpr int S = C::S, NTEAM = C::NTEAM, R = C::R, SLOT_DBL = C::SLOT_DBL, NI = C::NI, NJ = C::NJ, NJOB = C::NJOB;
+  constexpr int N = 8 * TG;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lk = lane & 3, lr = lane >> 2;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < R; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], S);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == GM_CONTRACT_WARPS) {
+    // ------------------------------------------------------------------------------------------ producer warp
+    int n = 0;
+    for (int task = it.t0; task < it.t1; ++task) {
+      const unsigned char* ga = A.gact + (size_t)task * A.ngroup;
+      const double* coef_t = A.coef + (size_t)task * A.task_stride;
+      for (int c0 = d.gbegin; c0 < d.gend; c0 += 32) {
+        const int idx = c0 + lane;
+        const int g = idx < d.gend ? A.glist[idx] : -1;
+        const bool active = g >= 0 && ga[g] != 0;
+        const int row = active ? A.grow[g] : 0;
+        const int nr = active ? GM_KSTEP * A.gk4[g] : 0;
+        unsigned mask = __ballot_sync(0xffffffffu, active);
+        while (mask) {
+          const int l = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const int r0 = __shfl_sync(0xffffffffu, row, l);
+          const int nr0 = __shfl_sync(0xffffffffu, nr, l);
+          if (lane == 0) {
+            const int s = n % R;
+            if (n >= R) mbar_wait(&empty[s], ((n / R) - 1) & 1);
+            tags[s] = GRAM_TAG_DATA;
+            double* dst = ring + (size_t)s * SLOT_DBL;
+            mbar_expect_tx(&full[s], (uint32_t)(SLOT_DBL * 8));
+            bulk_g2s(dst, coef_t + (size_t)r0 * GM_SB, (uint32_t)(nr0 * GM_SB * 8), &full[s]);
+            if (nr0 < 8 * TG) bulk_g2s(dst + nr0 * GM_SB, A.zeros, (uint32_t)((8 * TG - nr0) * GM_SB * 8), &full[s]);
+          }
+          ++n;
+        }
+      }
+      // one end-of-task marker per team (consecutive ring positions visit every team exactly once)
+      for (int k = 0; k < NTEAM; ++k, ++n) {
+        if (lane == 0) {
+          const int s = n % R;
+          if (n >= R) mbar_wait(&empty[s], ((n / R) - 1) & 1);
+          tags[s] = GRAM_TAG_END;
+          mbar_arrive(&full[s]);
+        }
+      }
+    }
+    return;
+  }
+
+  // ---------------------------------------------------------------------------------------------- consumer warps
+  const int team = warp / S, r = warp % S;
+  // role of this warp: which block(s) of H, which operand halves of a coefficient row (c+ at 0, c- at 64)
+  int blk = 0, aoff = 0, boff = 0, j0 = 0;
+  bool tilde = false;
+  if (S >= 4) {
+    blk = S == 12 ? r / 3 : r;
+    j0 = S == 12 ? (r % 3) * C::CW : 0;
+    aoff = blk == 1 ? 64 : 0;
+    boff = blk == 0 ? 0 : 64;
+    tilde = blk == 3;
+  }
+  const double sgn = (lk & 1) ? -1.0 : 1.0;
+  const int lane_off = lr * GM_SB + lk;
+
+  double acc[NJOB][NI][NJ][2];
+#pragma unroll
+  for (int q = 0; q < NJOB; ++q)
+#pragma unroll
+    for (int i = 0; i < NI; ++i)
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) acc[q][i][j][0] = acc[q][i][j][1] = 0.0;
+
+  int task = it.t0;
+  for (int n = team;; n += NTEAM) {
+    const int s = n % R;
+    mbar_wait(&full[s], (n / R) & 1);
+    const int tag = tags[s];
+    if (tag == GRAM_TAG_DATA) {
+      const double* st = ring + (size_t)s * SLOT_DBL + lane_off;
+      if constexpr (S == 1) {
+#pragma unroll 4
+        for (int ks = 0; ks < 16; ++ks) {
+          const double fp = st[4 * ks], fm = st[64 + 4 * ks];
+          const double ft = sgn * __shfl_xor_sync(0xffffffffu, fp, 1);
+          dmma884(acc[0][0][0][0], acc[0][0][0][1], fp, fp);   // H1
+          dmma884(acc[1][0][0][0], acc[1][0][0][1], fm, fm);   // H2
+          dmma884(acc[2][0][0][0], acc[2][0][0][1], fp, fm);   // H3
+          dmma884(acc[3][0][0][0], acc[3][0][0][1], ft, fm);   // H4
+        }
+      } else if constexpr (S == 2) {
+        // r = 0: H1 = (X+, X+), H2 = (X-, X-);  r = 1: H3 = (X+, X-), H4 = (X~+, X-)
+#pragma unroll 2
+        for (int ks = 0; ks < 16; ++ks) {
+          double fp[NI], fm[NI], a1[NI], b0[NI];
+#pragma unroll
+          for (int i = 0; i < NI; ++i) {
+            fp[i] = st[i * 8 * GM_SB + 4 * ks];
+            fm[i] = st[i * 8 * GM_SB + 64 + 4 * ks];
+            const double ft = sgn * __shfl_xor_sync(0xffffffffu, fp[i], 1);
+            a1[i] = r ? ft : fm[i];
+            b0[i] = r ? fm[i] : fp[i];
+          }
+#pragma unroll
+          for (int i = 0; i < NI; ++i)
+#pragma unroll
+            for (int j = 0; j < NI; ++j) {
+              dmma884(acc[0][i][j][0], acc[0][i][j][1], fp[i], b0[j]);
+              dmma884(acc[1][i][j][0], acc[1][i][j][1], a1[i], fm[j]);
+            }
+        }
+      } else {
+        const double* sa = st + aoff;
+        const double* sb = st + boff;
+#pragma unroll 2
+        for (int ks = 0; ks < 16; ++ks) {
+          double b[NJ];
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            int jt = j0 + j;
+            if (S == 12 && jt > TG - 1) jt = TG - 1;   // ragged last third: recompute the last column tile (not stored)
+            b[j] = sb[jt * 8 * GM_SB + 4 * ks];
+          }
+#pragma unroll
+          for (int i = 0; i < NI; ++i) {
+            double a = sa[i * 8 * GM_SB + 4 * ks];
+            const double at = sgn * __shfl_xor_sync(0xffffffffu, a, 1);
+            a = tilde ? at : a;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) dmma884(acc[0][i][j][0], acc[0][i][j][1], a, b[j]);
+          }
+        }
+      }
+    } else {
+      // end of task: this team's partial H -> global (fixed slot: summed in fixed order by k_gram_eval), then reset
+      double* hp = A.hpart + (size_t)task * A.hstride + d.hoff + (size_t)team * 4 * N * N;
+#pragma unroll
+      for (int q = 0; q < NJOB; ++q) {
+        int b = blk;
+        if (S == 1) b = q;
+        if (S == 2) b = q == 0 ? (r ? 2 : 0) : (r ? 3 : 1);
+#pragma unroll
+        for (int i = 0; i < NI; ++i)
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            const int jt = j0 + j;
+            if (jt < TG)
+              *reinterpret_cast<double2*>(hp + ((size_t)b * N + 8 * i + lr) * N + 8 * jt + 2 * lk) =
+                  make_double2(acc[q][i][j][0], acc[q][i][j][1]);
+            acc[q][i][j][0] = acc[q][i][j][1] = 0.0;
+          }
+      }
+      ++task;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+    if (tag != GRAM_TAG_DATA && task == it.t1) break;
+  }
+}
+
+__global__ void __launch_bounds__(GM_GRAM_THREADS, 1) k_gram(GramArgs A) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* ring = reinterpret_cast<double*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)GM_GRAM_RING_DBL * 8);
+  uint64_t* empty = full + GM_GRAM_MAX_SLOTS;
+  volatile int* tags = reinterpret_cast<volatile int*>(empty + GM_GRAM_MAX_SLOTS);
+  const GramItem it = A.items[blockIdx.x];
+  const GramDesc d = A.desc[it.desc];
+  switch (d.tg) {
+    case 1: gram_cta<1>(A, it, d, ring, full, empty, tags); break;
+    case 2: gram_cta<2>(A, it, d, ring, full, empty, tags); break;
+    case 3: gram_cta<3>(A, it, d, ring, full, empty, tags); break;
+    case 4: gram_cta<4>(A, it, d, ring, full, empty, tags); break;
+    case 6: gram_cta<6>(A, it, d, ring, full, empty, tags); break;
+    default: gram_cta<8>(A, it, d, ring, full, empty, tags); break;
+  }
+}
+
+// ================================================================================================ k_gram_sum
+// H[task][4][N][N] = sum of the partial Gram blocks of every (descriptor, team) in fixed order (deterministic).  One thread
+// per pair of adjacent columns; the partials of the teams of a descriptor are independent loads (latency overlapped).
+struct GramSumArgs {
+  int ndesc;
+  const GramDesc* desc;
+  const double* hpart;
+  long long hstride;
+  int N;          // 8 * largest class
+  double* hsum;   // [ntask][4][N][N]
+};
+
+__global__ void __launch_bounds__(256) k_gram_sum(GramSumArgs A) {
+  const int task = blockIdx.y;
+  const int N = A.N, half = N / 2;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 4 * N * half) return;
+  const int b = e / (N * half), n = (e / half) % N, c = 2 * (e % half);
+  const double* hp = A.hpart + (size_t)task * A.hstride;
+  double2 s = make_double2(0.0, 0.0);
+  for (int k = 0; k < A.ndesc; ++k) {
+    const GramDesc d = A.desc[k];
+    const int Nd = 8 * d.tg;
+    if (n < Nd && c < Nd) {
+      const double2* p = reinterpret_cast<const double2*>(hp + d.hoff + ((size_t)b * Nd + n) * Nd + c);
+      const size_t stride = (size_t)2 * Nd * Nd;   // 4 Nd^2 doubles per team
+      double2 v[12];
+#pragma unroll
+      for (int t = 0; t < 12; ++t) v[t] = t < d.nteam ? p[t * stride] : make_double2(0.0, 0.0);
+#pragma unroll
+      for (int t = 0; t < 12; ++t) {
+        s.x += v[t].x;
+        s.y += v[t].y;
+      }
+    }
+  }
+  *reinterpret_cast<double2*>(A.hsum + (((size_t)task * 4 + b) * N + n) * N + c) = s;
+}
+
+// ================================================================================================ k_gram_eval
+// Angle-stationary evaluation of the four quadratic forms.  CTA = (block of 96 angles, range of tasks); each warp owns 8
+// angles and keeps its p_n / q_n DMMA A-fragments in registers for the whole task range; H of the next task is fetched into
+// shared memory (cp.async, double-buffered when it fits) while the current one is multiplied:  D = L^T H (DMMA), then
+// out = rowsum(D .* R) with the right factors taken from the same fragments by warp shuffles.
+struct GramEvalArgs {
+  int ntask, tasks_per_cta;
+  const double* hsum;   // [ntask][4][N][N]
+  int N;                // 8 * largest class
+  int ntile;            // column tiles that can be non-zero
+  int nk4;              // k4 steps over the rows of H that can be non-zero (<= 16, 4 nk4 <= nrows)
+  int nbuf;             // shared-memory buffers for H (1 or 2)
+  const double* T;      // p/q angle table of the bin, [2][nrows][GM_TROW]
+  int nrows;
+  double* part;         // [ntask][nchunk][4][GM_NANG_PAD]
+  int nchunk, chunk;
+};
+
+constexpr int GM_GRAM_EVAL_THREADS = 384;
+constexpr int GM_GRAM_EVAL_SMEM_MAX = 220 * 1024;
+constexpr int GM_GRAM_NK4_MAX = 2 * GM_GRAM_MAX_TG;
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+
+__global__ void __launch_bounds__(GM_GRAM_EVAL_THREADS, 1) k_gram_eval(GramEvalArgs A) {
+  extern __shared__ __align__(16) double Hs[];   // [nbuf][4][N][NP]
+  const int N = A.N, NP = N + 4;
+  const size_t buf_dbl = (size_t)4 * N * NP;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lk = lane & 3, lr = lane >> 2;
+  const int mt = blockIdx.x * 12 + warp;          // m-tile of 8 angles in the padded 384-angle space
+  const int half = mt / 24, acol = (mt % 24) * 8;
+  const int t0 = blockIdx.y * A.tasks_per_cta, t1 = min(A.ntask, t0 + A.tasks_per_cta);
+
+  auto prefetch = [&](int task, int buf) {
+    const double* src = A.hsum + (size_t)task * 4 * N * N;
+    double* dst = Hs + (size_t)buf * buf_dbl;
+    const int halfN = N / 2;
+    for (int e = threadIdx.x; e < 4 * N * halfN; e += blockDim.x) {
+      const int row = e / halfN, c = 2 * (e % halfN);
+      cp_async16(dst + (size_t)row * NP + c, src + (size_t)row * N + c);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (t0 < t1) prefetch(t0, 0);
+
+  // A fragments: lane (lr, lk) holds L[angle acol + lr][n = 4 ks + lk] for p (ap) and q (aq)
+  double ap[GM_GRAM_NK4_MAX], aq[GM_GRAM_NK4_MAX];
+  {
+    const double* Th = A.T + (size_t)half * A.nrows * GM_TROW + acol + lr;
+#pragma unroll
+    for (int ks = 0; ks < GM_GRAM_NK4_MAX; ++ks) {
+      ap[ks] = aq[ks] = 0.0;
+      if (ks < A.nk4) {
+        ap[ks] = Th[(size_t)(4 * ks + lk) * GM_TROW];
+        aq[ks] = Th[(size_t)(4 * ks + lk) * GM_TROW + GM_LAH];
+      }
+    }
+  }
+  const int src0 = lr * 4 + 2 * (lk & 1);
+  const bool hi = (lk >> 1) != 0;
+
+  for (int task = t0; task < t1; ++task) {
+    const int buf = A.nbuf == 2 ? ((task - t0) & 1) : 0;
+    if (A.nbuf == 2 && task + 1 < t1) {
+      prefetch(task + 1, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const double* Hb = Hs + (size_t)buf * buf_dbl + (size_t)lk * NP + lr;
+    double out[4];
+#pragma unroll
+    for (int pair = 0; pair < 2; ++pair) {
+      // pair 0: H1 (left p, right p) and H3 (left p, right q);  pair 1: H2 (left q, right q) and H4 (left p, right q)
+      const int b0 = pair, b1 = pair + 2;
+      double acc0[GM_GRAM_MAX_TG][2], acc1[GM_GRAM_MAX_TG][2];
+#pragma unroll
+      for (int j = 0; j < GM_GRAM_MAX_TG; ++j) acc0[j][0] = acc0[j][1] = acc1[j][0] = acc1[j][1] = 0.0;
+      const double* H0 = Hb + (size_t)b0 * N * NP;
+      const double* H1 = Hb + (size_t)b1 * N * NP;
+#pragma unroll
+      for (int ks = 0; ks < GM_GRAM_NK4_MAX; ++ks)
+        if (ks < A.nk4) {
+          const double a0 = pair == 0 ? ap[ks] : aq[ks];
+          const double a1 = ap[ks];
+#pragma unroll
+          for (int j = 0; j < GM_GRAM_MAX_TG; ++j)
+            if (j < A.ntile) {
+              dmma884(acc0[j][0], acc0[j][1], a0, H0[(size_t)4 * ks * NP + 8 * j]);
+              dmma884(acc1[j][0], acc1[j][1], a1, H1[(size_t)4 * ks * NP + 8 * j]);
+            }
+        }
+      // right factors R[angle][c], c = 8 j + 2 lk (+1): held by lane (lr, c % 4) in fragment ks = c / 4
+      double o0 = 0.0, o1 = 0.0;
+#pragma unroll
+      for (int j = 0; j < GM_GRAM_MAX_TG; ++j)
+        if (j < A.ntile) {
+          const double pe0 = __shfl_sync(0xffffffffu, ap[2 * j], src0), pe1 = __shfl_sync(0xffffffffu, ap[2 * j + 1], src0);
+          const double po0 = __shfl_sync(0xffffffffu, ap[2 * j], src0 + 1), po1 = __shfl_sync(0xffffffffu, ap[2 * j + 1], src0 + 1);
+          const double qe0 = __shfl_sync(0xffffffffu, aq[2 * j], src0), qe1 = __shfl_sync(0xffffffffu, aq[2 * j + 1], src0);
+          const double qo0 = __shfl_sync(0xffffffffu, aq[2 * j], src0 + 1), qo1 = __shfl_sync(0xffffffffu, aq[2 * j + 1], src0 + 1);
+          const double pc = hi ? pe1 : pe0, pc1 = hi ? po1 : po0;   // p at columns c, c + 1
+          const double qc = hi ? qe1 : qe0, qc1 = hi ? qo1 : qo0;   // q at columns c, c + 1
+          const double r0a = pair == 0 ? pc : qc, r0b = pair == 0 ? pc1 : qc1;   // right factor of block b0
+          o0 = fma(acc0[j][0], r0a, fma(acc0[j][1], r0b, o0));
+          o1 = fma(acc1[j][0], qc, fma(acc1[j][1], qc1, o1));                     // blocks H3, H4: right factor q
+        }
+      o0 += __shfl_xor_sync(0xffffffffu, o0, 1);
+      o0 += __shfl_xor_sync(0xffffffffu, o0, 2);
+      o1 += __shfl_xor_sync(0xffffffffu, o1, 1);
+      o1 += __shfl_xor_sync(0xffffffffu, o1, 2);
+      out[b0] = o0;
+      out[b1] = o1;
+    }
+    if (lk == 0) {
+      double* o = A.part + (((size_t)task * A.nchunk + A.chunk) * 4) * GM_NANG_PAD + half * GM_HALF_ANG + acol + lr;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) o[(size_t)b * GM_NANG_PAD] = out[b];
+    }
+    __syncthreads();   // everyone is done with `buf` before the next prefetch overwrites it
+    if (A.nbuf == 1 && task + 1 < t1) prefetch(task + 1, 0);
+  }
+}

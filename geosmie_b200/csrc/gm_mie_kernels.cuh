@@ -424,8 +424,10 @@ struct ContractArgs {
   const int* grow;
   const int* gk4;
   const unsigned char* gact;          // [ntask][ngroup]
+  const unsigned char* gskip;         // [ngroup] or null: 1 = group is handled by the Gram path (gm_gram.cuh)
   const int* chunk_start;             // [nchunk + 1] group boundaries
-  double* part;                       // [ntask][nchunk][4][GM_NANG_PAD]
+  double* part;                       // [ntask][nchunk_total][4][GM_NANG_PAD]
+  int nchunk_total;                   // nchunk + 1 when the Gram path adds its own slot of partial sums
   // per-particle variant
   double* s12;                        // [ntask][nx][nang][4]
   int nx, nang;
@@ -462,7 +464,10 @@ __global__ void __launch_bounds__(GM_CONTRACT_THREADS, 1) k_contract(ContractArg
   const int ng = ce - cs;
   {
     const unsigned char* gact = A.gact + (size_t)task * A.ngroup;
-    for (int g = threadIdx.x; g < ng; g += blockDim.x) meta[g] = make_int2(gact[cs + g] ? A.gk4[cs + g] : 0, A.grow[cs + g]);
+    for (int g = threadIdx.x; g < ng; g += blockDim.x) {
+      const bool on = gact[cs + g] && !(A.gskip && A.gskip[cs + g]);
+      meta[g] = make_int2(on ? A.gk4[cs + g] : 0, A.grow[cs + g]);
+    }
   }
   __syncthreads();
   int nsteps = 0;
@@ -588,7 +593,7 @@ __global__ void __launch_bounds__(GM_CONTRACT_THREADS, 1) k_contract(ContractArg
     }
   }
   if (!PER_PARTICLE) {
-    double* out = A.part + ((size_t)task * A.nchunk + chunk) * 4 * GM_NANG_PAD + half * GM_HALF_ANG + a0 + lr;
+    double* out = A.part + ((size_t)task * A.nchunk_total + chunk) * 4 * GM_NANG_PAD + half * GM_HALF_ANG + a0 + lr;
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll

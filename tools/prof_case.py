@@ -7,6 +7,8 @@ from geosmie_b200 import _lib, dointegration as DI, workloads
 sp, b, ncell = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
 elide = "--elide" in sys.argv
 cells = [(li, rhi) for li in range(0, 61, 7) for rhi in range(0, 36, 5)][:ncell]
+if ncell > len(cells):
+    cells = [(li, rhi) for li in range(61) for rhi in range(36)][:ncell]
 plan = workloads.bin_plan(sp, b, cells=cells)
 h = _lib.Handle.get(0)
 cost = np.cos(np.radians(DI.table_angles()))
