@@ -68,10 +68,11 @@ def load():
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("GEOSMIE_B200_LIB", LIB_PATH)   # another build of the same library (kernel tuning experiments)
+        if not os.path.exists(path):
             raise GeosmieError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` or "
-                               "`make -C geosmie_b200/csrc` -- there is no CPU fallback" % LIB_PATH)
-        lib = C.CDLL(LIB_PATH)
+                               "`make -C geosmie_b200/csrc` -- there is no CPU fallback" % path)
+        lib = C.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype = res
@@ -199,6 +200,7 @@ class Table:
         # GM_F_NO_GRAM: force the per-angle contraction for every particle group (ablation / cross-check of the Gram path)
         self.no_gram = os.environ.get("GEOSMIE_NO_GRAM", "0") not in ("", "0")
 
+
     def _flags(self, elide):
         return (F_ELIDE_ZERO_WEIGHT if elide else 0) | (F_NO_GRAM if self.no_gram else 0)
 
@@ -325,8 +327,10 @@ class Table:
     def last_kernel_ms(self):
         a, b, c = C.c_double(), C.c_double(), C.c_double()
         check(self.lib.gm_table_last_kernel_ms(self.t, C.byref(a), C.byref(b), C.byref(c)))
-        ms, n = np.zeros(5), np.zeros(5, dtype=np.int32)
+        ms, n = np.zeros(8), np.zeros(8, dtype=np.int32)
         check(self.lib.gm_table_last_kernel_ms_ex(self.t, ptr(ms), ptr(n)))
-        return {"coeff": a.value, "contract": b.value, "finalize": c.value,
-                "k_contract": ms[1], "k_gram": ms[3], "k_gram_eval": ms[4],
-                "launches": dict(zip(("k_coeff", "k_contract", "k_finalize", "k_gram", "k_gram_eval"), n.tolist()))}
+        names = ("k_coeff", "k_contract", "k_finalize", "k_gram", "k_gram_sum_eval")
+        out = {"coeff": a.value, "contract": b.value, "finalize": c.value}
+        out.update({k: float(v) for k, v in zip(names, ms)})
+        out["launches"] = dict(zip(names, n.tolist()))
+        return out

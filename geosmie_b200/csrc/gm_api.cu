@@ -44,7 +44,14 @@ extern "C" int gm_init(int device, gm_handle_t* out) {
   GM_CUDA_TRY(cudaFuncSetAttribute(k_contract<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   GM_CUDA_TRY(cudaFuncSetAttribute(k_contract<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   GM_CUDA_TRY(cudaFuncSetAttribute(k_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_GRAM_SMEM));
-  GM_CUDA_TRY(cudaFuncSetAttribute(k_gram_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_GRAM_EVAL_SMEM_MAX));
+  GM_CUDA_TRY(cudaFuncSetAttribute(k_gram_eval<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_GRAM_EVAL_SMEM_MAX));
+  GM_CUDA_TRY(cudaFuncSetAttribute(k_gram_eval<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_GRAM_EVAL_SMEM_MAX));
+  GM_CUDA_TRY(cudaFuncSetAttribute(k_gram_eval<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_GRAM_EVAL_SMEM_MAX));
+  GM_CUDA_TRY(cudaFuncSetAttribute(k_gram_eval<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_GRAM_EVAL_SMEM_MAX));
+  GM_CUDA_TRY(cudaFuncSetAttribute(k_gram_eval<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_GRAM_EVAL_SMEM_MAX));
+  GM_CUDA_TRY(cudaFuncSetAttribute(k_gram_eval<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_GRAM_EVAL_SMEM_MAX));
+  GM_CUDA_TRY(cudaFuncSetAttribute(k_gram_eval<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_GRAM_EVAL_SMEM_MAX));
+  GM_CUDA_TRY(cudaFuncSetAttribute(k_gram_eval<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_GRAM_EVAL_SMEM_MAX));
   *out = h;
   return GM_OK;
 }
@@ -310,7 +317,7 @@ struct gm_table_s {
   std::vector<double> hx;
   std::vector<int32_t> hnmax;
   DevBuf T, cost, dr, psd_par, psd_frac;
-  DevBuf g_list, g_skip, g_zeros, g_desc, g_items, g_hpart, g_hsum;   // Gram path (gm_gram.cuh)
+  DevBuf g_list, g_skip, g_desc, g_items, g_hpart, g_hsum;   // Gram path (gm_gram.cuh)
   DevBuf c_ab, c_scratch, c_soff, c_aboff, c_ratio;   // coated-sphere table path
   // fused GSF stage (gm_table_set_gsf): moments of every finished batch are expanded and downloaded behind the kernels
   std::vector<double> gsf_ang;
@@ -359,14 +366,12 @@ extern "C" int gm_table_create(gm_handle_t h, int nx, const double* x, const int
   GM_CUDA_TRY(cudaMemcpyAsync(t->cost.p, cos_theta, sizeof(double) * nang, cudaMemcpyHostToDevice, st));
   GM_CUDA_TRY(cudaMemsetAsync(t->T.p, 0, sizeof(double) * GM_NHALF * (size_t)t->nrows * GM_TROW, st));
   if (!t->G.glist.empty()) {
-    if ((rc = t->g_list.ensure(sizeof(int) * t->G.glist.size())) || (rc = t->g_skip.ensure(t->G.ngroup)) ||
-        (rc = t->g_zeros.ensure(sizeof(double) * GM_GRAM_ZERO_DBL))) {
+    if ((rc = t->g_list.ensure(sizeof(int) * t->G.glist.size())) || (rc = t->g_skip.ensure(t->G.ngroup))) {
       delete t;
       return rc;
     }
     GM_CUDA_TRY(cudaMemcpyAsync(t->g_list.p, t->G.glist.data(), sizeof(int) * t->G.glist.size(), cudaMemcpyHostToDevice, st));
     GM_CUDA_TRY(cudaMemcpyAsync(t->g_skip.p, t->G.gskip.data(), t->G.ngroup, cudaMemcpyHostToDevice, st));
-    GM_CUDA_TRY(cudaMemsetAsync(t->g_zeros.p, 0, sizeof(double) * GM_GRAM_ZERO_DBL, st));
   }
   k_bessel<<<(nx + 127) / 128, 128, 0, st>>>(nx, t->D.x.as<double>(), t->D.nmax.as<int>(), t->D.gboff.as<long long>(),
                                              t->D.psi.as<double>(), t->D.chi.as<double>());
@@ -382,7 +387,7 @@ extern "C" int gm_table_destroy(gm_table_t t) {
   if (!t) return GM_OK;
   cudaSetDevice(t->h->device);
   t->D.release();
-  for (DevBuf* b : {&t->g_hsum, &t->g_list, &t->g_skip, &t->g_zeros, &t->g_desc, &t->g_items, &t->g_hpart, &t->gsf_coef, &t->gsf_cnorm, &t->c_ab, &t->c_scratch, &t->c_soff, &t->c_aboff, &t->c_ratio, &t->dr, &t->psd_par, &t->psd_frac, &t->T, &t->cost, &t->coef, &t->gact, &t->scal_part, &t->part, &t->chunk_start, &t->mz, &t->mrel, &t->wphase,
+  for (DevBuf* b : {&t->g_hsum, &t->g_list, &t->g_skip, &t->g_desc, &t->g_items, &t->g_hpart, &t->gsf_coef, &t->gsf_cnorm, &t->c_ab, &t->c_scratch, &t->c_soff, &t->c_aboff, &t->c_ratio, &t->dr, &t->psd_par, &t->psd_frac, &t->T, &t->cost, &t->coef, &t->gact, &t->scal_part, &t->part, &t->chunk_start, &t->mz, &t->mrel, &t->wphase,
                     &t->wscal, &t->out_scal, &t->out_phase, &t->stats, &t->q, &t->s12})
     b->release();
   for (auto& e : t->evpool) cudaEventDestroy(e);
@@ -463,15 +468,18 @@ extern "C" int gm_table_last_kernel_ms(gm_table_t t, double* a, double* b, doubl
   return GM_OK;
 }
 
-// per-kernel split of the last run: ms[0..4] = k_coeff, k_contract, k_finalize, k_gram, k_gram_eval; n[0..4] = launches of each
-extern "C" int gm_table_last_kernel_ms_ex(gm_table_t t, double ms[5], int32_t n[5]) {
+// per-kernel split of the last run: ms[0..4] = k_coeff, k_contract, k_finalize, k_gram, k_gram_sum + k_gram_eval;
+// n[0..4] = event-bracketed launch groups of each
+extern "C" int gm_table_last_kernel_ms_ex(gm_table_t t, double ms[8], int32_t n[8]) {
   int rc = gm_table_last_kernel_ms(t, nullptr, nullptr, nullptr);
   if (rc) return rc;
   if (ms) {
     ms[0] = t->ms_coeff; ms[1] = t->ms_contract; ms[2] = t->ms_finalize; ms[3] = t->ms_gram; ms[4] = t->ms_gram_eval;
+    ms[5] = ms[6] = ms[7] = 0;
   }
   if (n) {
     n[0] = t->n_coeff; n[1] = t->n_contract; n[2] = t->n_finalize; n[3] = t->n_gram; n[4] = t->n_gram_eval;
+    n[5] = n[6] = n[7] = 0;
   }
   return GM_OK;
 }
@@ -681,6 +689,9 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
     A.scal_part = t->scal_part.as<double>();
     A.q = d_q ? d_q + (size_t)t0 * G.nx * 6 : nullptr;
     A.stats = t->stats.as<unsigned long long>();
+    const GramPlan* P = nullptr;
+    for (auto& q : plans)
+      if (q.nt == nt) P = &q;
     if ((rc = ev_mark(t, 0))) return rc;
     if (d_core_ratio) {
       // mz carries the core index m1 = sqrt(eps1), mrel the shell index m2 = sqrt(eps2) (gm_mie_eval convention)
@@ -728,9 +739,6 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
       if ((rc = ev_mark(t, 1))) return rc;
     }
     if (use_gram) {
-      const GramPlan* P = nullptr;
-      for (auto& q : plans)
-        if (q.nt == nt) P = &q;
       GramArgs GA;
       memset(&GA, 0, sizeof(GA));
       GA.ngroup = G.ngroup;
@@ -742,18 +750,20 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
       GA.gact = t->gact.as<unsigned char>();
       GA.coef = t->coef.as<double>();
       GA.task_stride = task_stride;
-      GA.zeros = t->g_zeros.as<double>();
       GA.hpart = t->g_hpart.as<double>();
       GA.hstride = P->hstride;
-      if ((rc = ev_mark(t, 3))) return rc;
-      k_gram<<<P->nitem, GM_GRAM_THREADS, GM_GRAM_SMEM, st>>>(GA);
-      GM_LAUNCH_CHECK(h);
-      if ((rc = ev_mark(t, 3))) return rc;
+      if (P->nitem > 0) {
+        if ((rc = ev_mark(t, 3))) return rc;
+        k_gram<<<P->nitem, GM_GRAM_THREADS, GM_GRAM_SMEM, st>>>(GA);
+        GM_LAUNCH_CHECK(h);
+        if ((rc = ev_mark(t, 3))) return rc;
+      }
       const int N = 8 * G.gram_tgmax;
       GramSumArgs SA;
       memset(&SA, 0, sizeof(SA));
       SA.ndesc = P->ndesc;
-      SA.desc = GA.desc;
+      GM_REQUIRE(P->ndesc <= GM_GRAM_SUM_MAXDESC, "too many Gram descriptors");
+      for (int k = 0; k < P->ndesc; ++k) SA.desc[k] = all_desc[P->desc0 + k];
       SA.hpart = GA.hpart;
       SA.hstride = P->hstride;
       SA.N = N;
@@ -776,7 +786,17 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
       if ((rc = ev_mark(t, 4))) return rc;
       k_gram_sum<<<dim3((2 * N * N + 255) / 256, nt), 256, 0, st>>>(SA);
       GM_LAUNCH_CHECK(h);
-      k_gram_eval<<<dim3(4, (nt + EA.tasks_per_cta - 1) / EA.tasks_per_cta), GM_GRAM_EVAL_THREADS, EA.nbuf * hbytes, st>>>(EA);
+      const dim3 egrid(4, (nt + EA.tasks_per_cta - 1) / EA.tasks_per_cta);
+      switch (EA.ntile) {
+        case 1: k_gram_eval<1><<<egrid, GM_GRAM_EVAL_THREADS, EA.nbuf * hbytes, st>>>(EA); break;
+        case 2: k_gram_eval<2><<<egrid, GM_GRAM_EVAL_THREADS, EA.nbuf * hbytes, st>>>(EA); break;
+        case 3: k_gram_eval<3><<<egrid, GM_GRAM_EVAL_THREADS, EA.nbuf * hbytes, st>>>(EA); break;
+        case 4: k_gram_eval<4><<<egrid, GM_GRAM_EVAL_THREADS, EA.nbuf * hbytes, st>>>(EA); break;
+        case 5: k_gram_eval<5><<<egrid, GM_GRAM_EVAL_THREADS, EA.nbuf * hbytes, st>>>(EA); break;
+        case 6: k_gram_eval<6><<<egrid, GM_GRAM_EVAL_THREADS, EA.nbuf * hbytes, st>>>(EA); break;
+        case 7: k_gram_eval<7><<<egrid, GM_GRAM_EVAL_THREADS, EA.nbuf * hbytes, st>>>(EA); break;
+        default: k_gram_eval<8><<<egrid, GM_GRAM_EVAL_THREADS, EA.nbuf * hbytes, st>>>(EA); break;
+      }
       GM_LAUNCH_CHECK(h);
       if ((rc = ev_mark(t, 4))) return rc;
     }

@@ -16,9 +16,9 @@
 //   k_gram       CTA = (class of particle groups, range of tasks).  Groups are classed by tg = ceil(max nmax / 8) (number of
 //                8-row DMMA tiles); a class fixes how the 4 tg^2 accumulator tiles are split over `S` warps (a team) and how
 //                many teams (12 / S) work on different groups at the same time.  One TMA producer warp streams the
-//                coefficient rows of each group (contiguous in the stream written by k_coeff) into a shared-memory ring,
-//                zero-filling the slot up to 8 tg rows from a zero page; end-of-task markers travel through the same ring, so
-//                a CTA runs through several tasks without any CTA-wide barrier.
+//                coefficient rows of each group (contiguous in the stream written by k_coeff) into a shared-memory ring
+//                (one lane of the producer warp per team); end-of-task markers travel through the same ring, so a CTA runs
+//                through several tasks without any CTA-wide barrier.
 //   k_gram_eval  CTA = task: sums the partial H (fixed order: deterministic), D = L^T H on DMMA, out = rowsum(D .* R).
 #pragma once
 #include "gm_mie_kernels.cuh"
@@ -27,8 +27,7 @@ constexpr int GM_GRAM_MAX_TG = 8;                                    // groups w
 constexpr int GM_GRAM_THREADS = (GM_CONTRACT_WARPS + 1) * 32;        // 12 consumer warps + 1 producer warp
 constexpr int GM_GRAM_MAX_SLOTS = 24;
 constexpr int GM_GRAM_RING_DBL = GM_GRAM_MAX_SLOTS * 8 * GM_SB;      // 202 752 B
-constexpr int GM_GRAM_SMEM = GM_GRAM_RING_DBL * 8 + 2 * GM_GRAM_MAX_SLOTS * 8 + GM_GRAM_MAX_SLOTS * 4;
-constexpr int GM_GRAM_ZERO_DBL = 8 * GM_GRAM_MAX_TG * GM_SB;         // zero page (doubles)
+constexpr int GM_GRAM_SMEM = GM_GRAM_RING_DBL * 8 + 2 * GM_GRAM_MAX_SLOTS * 8 + GM_GRAM_MAX_SLOTS * 4 + 64 * 4;
 
 struct GramDesc {
   int tg;          // template class: 1, 2, 3, 4, 6 or 8 tiles
@@ -50,7 +49,6 @@ struct GramArgs {
   const unsigned char* gact;   // [ntask][ngroup]
   const double* coef;
   long long task_stride;
-  const double* zeros;
   double* hpart;               // [ntask][hstride]
   long long hstride;
 };
@@ -69,13 +67,14 @@ struct GramCfg {
   static_assert(R <= GM_GRAM_MAX_SLOTS && R * SLOT_DBL <= GM_GRAM_RING_DBL, "ring does not fit");
 };
 
-constexpr int GRAM_TAG_DATA = 0, GRAM_TAG_END = 1;
-
+// Ring protocol.  Team t owns the DEPTH slots [t DEPTH, (t + 1) DEPTH); lane t of the producer warp feeds them (the lanes run
+// independently, so a slow team never blocks the others).  tags[slot] = number of coefficient rows copied into the slot
+// (rows beyond are treated as zero by the consumers, nothing is copied for them), 0 = end-of-task marker.
 template <int TG>
 __device__ __forceinline__ void gram_cta(const GramArgs& A, const GramItem it, const GramDesc d, double* ring, uint64_t* full,
-                                         uint64_t* empty, volatile int* tags) {
+                                         uint64_t* empty, volatile int* tags, volatile int* cand) {
   using C = GramCfg<TG>;
-  constexpr int S = C::S, NTEAM = C::NTEAM, R = C::R, SLOT_DBL = C::SLOT_DBL, NI = C::NI, NJ = C::NJ, NJOB = C::NJOB;
+  constexpr int S = C::S, NTEAM = C::NTEAM, DEPTH = C::DEPTH, R = C::R, SLOT_DBL = C::SLOT_DBL, NI = C::NI, NJ = C::NJ, NJOB = C::NJOB;
   constexpr int N = 8 * TG;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int lk = lane & 3, lr = lane >> 2;
@@ -91,7 +90,14 @@ __device__ __forceinline__ void gram_cta(const GramArgs& A, const GramItem it, c
 
   if (warp == GM_CONTRACT_WARPS) {
     // ------------------------------------------------------------------------------------------ producer warp
-    int n = 0;
+    int m = 0;        // slots produced so far by this lane (for team `lane`)
+    int nbase = 0;    // active groups handed out so far: group number n goes to team n % NTEAM
+    auto acquire = [&]() -> int {
+      const int s = lane * DEPTH + m % DEPTH;
+      if (m >= DEPTH) mbar_wait(&empty[s], ((m / DEPTH) - 1) & 1);
+      ++m;
+      return s;
+    };
     for (int task = it.t0; task < it.t1; ++task) {
       const unsigned char* ga = A.gact + (size_t)task * A.ngroup;
       const double* coef_t = A.coef + (size_t)task * A.task_stride;
@@ -99,34 +105,30 @@ __device__ __forceinline__ void gram_cta(const GramArgs& A, const GramItem it, c
         const int idx = c0 + lane;
         const int g = idx < d.gend ? A.glist[idx] : -1;
         const bool active = g >= 0 && ga[g] != 0;
-        const int row = active ? A.grow[g] : 0;
-        const int nr = active ? GM_KSTEP * A.gk4[g] : 0;
-        unsigned mask = __ballot_sync(0xffffffffu, active);
-        while (mask) {
-          const int l = __ffs(mask) - 1;
-          mask &= mask - 1;
-          const int r0 = __shfl_sync(0xffffffffu, row, l);
-          const int nr0 = __shfl_sync(0xffffffffu, nr, l);
-          if (lane == 0) {
-            const int s = n % R;
-            if (n >= R) mbar_wait(&empty[s], ((n / R) - 1) & 1);
-            tags[s] = GRAM_TAG_DATA;
-            double* dst = ring + (size_t)s * SLOT_DBL;
-            mbar_expect_tx(&full[s], (uint32_t)(SLOT_DBL * 8));
-            bulk_g2s(dst, coef_t + (size_t)r0 * GM_SB, (uint32_t)(nr0 * GM_SB * 8), &full[s]);
-            if (nr0 < 8 * TG) bulk_g2s(dst + nr0 * GM_SB, A.zeros, (uint32_t)((8 * TG - nr0) * GM_SB * 8), &full[s]);
+        const unsigned mask = __ballot_sync(0xffffffffu, active);
+        if (active) {
+          const int rank = __popc(mask & ((1u << lane) - 1u));
+          cand[rank] = A.grow[g];
+          cand[32 + rank] = GM_KSTEP * A.gk4[g];
+        }
+        __syncwarp();
+        const int cnt = __popc(mask);
+        if (lane < NTEAM) {
+          for (int k = (lane + NTEAM - nbase % NTEAM) % NTEAM; k < cnt; k += NTEAM) {
+            const int row = cand[k], nr = cand[32 + k];
+            const int s = acquire();
+            tags[s] = nr;
+            mbar_expect_tx(&full[s], (uint32_t)(nr * GM_SB * 8));
+            bulk_g2s(ring + (size_t)s * SLOT_DBL, coef_t + (size_t)row * GM_SB, (uint32_t)(nr * GM_SB * 8), &full[s]);
           }
-          ++n;
         }
+        nbase += cnt;
+        __syncwarp();
       }
-      // one end-of-task marker per team (consecutive ring positions visit every team exactly once)
-      for (int k = 0; k < NTEAM; ++k, ++n) {
-        if (lane == 0) {
-          const int s = n % R;
-          if (n >= R) mbar_wait(&empty[s], ((n / R) - 1) & 1);
-          tags[s] = GRAM_TAG_END;
-          mbar_arrive(&full[s]);
-        }
+      if (lane < NTEAM) {   // end-of-task marker of this team
+        const int s = acquire();
+        tags[s] = 0;
+        mbar_arrive(&full[s]);
       }
     }
     return;
@@ -156,16 +158,17 @@ __device__ __forceinline__ void gram_cta(const GramArgs& A, const GramItem it, c
       for (int j = 0; j < NJ; ++j) acc[q][i][j][0] = acc[q][i][j][1] = 0.0;
 
   int task = it.t0;
-  for (int n = team;; n += NTEAM) {
-    const int s = n % R;
-    mbar_wait(&full[s], (n / R) & 1);
-    const int tag = tags[s];
-    if (tag == GRAM_TAG_DATA) {
+  for (int m = 0;; ++m) {
+    const int s = team * DEPTH + m % DEPTH;
+    mbar_wait(&full[s], (m / DEPTH) & 1);
+    const int nr = tags[s];
+    if (nr > 0) {
       const double* st = ring + (size_t)s * SLOT_DBL + lane_off;
+      const int nrl = nr - lr;   // row 8 i + lr of the slot was copied iff 8 i < nrl (otherwise it is a zero row)
       if constexpr (S == 1) {
 #pragma unroll 4
         for (int ks = 0; ks < 16; ++ks) {
-          const double fp = st[4 * ks], fm = st[64 + 4 * ks];
+          const double fp = 0 < nrl ? st[4 * ks] : 0.0, fm = 0 < nrl ? st[64 + 4 * ks] : 0.0;
           const double ft = sgn * __shfl_xor_sync(0xffffffffu, fp, 1);
           dmma884(acc[0][0][0][0], acc[0][0][0][1], fp, fp);   // H1
           dmma884(acc[1][0][0][0], acc[1][0][0][1], fm, fm);   // H2
@@ -179,8 +182,8 @@ __device__ __forceinline__ void gram_cta(const GramArgs& A, const GramItem it, c
           double fp[NI], fm[NI], a1[NI], b0[NI];
 #pragma unroll
           for (int i = 0; i < NI; ++i) {
-            fp[i] = st[i * 8 * GM_SB + 4 * ks];
-            fm[i] = st[i * 8 * GM_SB + 64 + 4 * ks];
+            fp[i] = 8 * i < nrl ? st[i * 8 * GM_SB + 4 * ks] : 0.0;
+            fm[i] = 8 * i < nrl ? st[i * 8 * GM_SB + 64 + 4 * ks] : 0.0;
             const double ft = sgn * __shfl_xor_sync(0xffffffffu, fp[i], 1);
             a1[i] = r ? ft : fm[i];
             b0[i] = r ? fm[i] : fp[i];
@@ -196,18 +199,18 @@ __device__ __forceinline__ void gram_cta(const GramArgs& A, const GramItem it, c
       } else {
         const double* sa = st + aoff;
         const double* sb = st + boff;
+        const int jlast = (S == 12 && j0 + NJ > TG) ? TG - 1 - j0 : NJ - 1;   // ragged last third: recompute the last column tile (not stored)
 #pragma unroll 2
         for (int ks = 0; ks < 16; ++ks) {
           double b[NJ];
 #pragma unroll
           for (int j = 0; j < NJ; ++j) {
-            int jt = j0 + j;
-            if (S == 12 && jt > TG - 1) jt = TG - 1;   // ragged last third: recompute the last column tile (not stored)
-            b[j] = sb[jt * 8 * GM_SB + 4 * ks];
+            const int jt = j0 + (j < jlast ? j : jlast);
+            b[j] = 8 * jt < nrl ? sb[jt * 8 * GM_SB + 4 * ks] : 0.0;
           }
 #pragma unroll
           for (int i = 0; i < NI; ++i) {
-            double a = sa[i * 8 * GM_SB + 4 * ks];
+            double a = 8 * i < nrl ? sa[i * 8 * GM_SB + 4 * ks] : 0.0;
             const double at = sgn * __shfl_xor_sync(0xffffffffu, a, 1);
             a = tilde ? at : a;
 #pragma unroll
@@ -216,7 +219,7 @@ __device__ __forceinline__ void gram_cta(const GramArgs& A, const GramItem it, c
         }
       }
     } else {
-      // end of task: this team's partial H -> global (fixed slot: summed in fixed order by k_gram_eval), then reset
+      // end of task: this team's partial H -> global (fixed slot: summed in fixed order by k_gram_sum), then reset
       double* hp = A.hpart + (size_t)task * A.hstride + d.hoff + (size_t)team * 4 * N * N;
 #pragma unroll
       for (int q = 0; q < NJOB; ++q) {
@@ -227,9 +230,9 @@ __device__ __forceinline__ void gram_cta(const GramArgs& A, const GramItem it, c
         for (int i = 0; i < NI; ++i)
 #pragma unroll
           for (int j = 0; j < NJ; ++j) {
-            const int jt = j0 + j;
-            if (jt < TG)
-              *reinterpret_cast<double2*>(hp + ((size_t)b * N + 8 * i + lr) * N + 8 * jt + 2 * lk) =
+            const int jc = j0 + j;
+            if (jc < TG)
+              *reinterpret_cast<double2*>(hp + ((size_t)b * N + 8 * i + lr) * N + 8 * jc + 2 * lk) =
                   make_double2(acc[q][i][j][0], acc[q][i][j][1]);
             acc[q][i][j][0] = acc[q][i][j][1] = 0.0;
           }
@@ -238,7 +241,7 @@ __device__ __forceinline__ void gram_cta(const GramArgs& A, const GramItem it, c
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
-    if (tag != GRAM_TAG_DATA && task == it.t1) break;
+    if (nr == 0 && task == it.t1) break;
   }
 }
 
@@ -248,24 +251,26 @@ __global__ void __launch_bounds__(GM_GRAM_THREADS, 1) k_gram(GramArgs A) {
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)GM_GRAM_RING_DBL * 8);
   uint64_t* empty = full + GM_GRAM_MAX_SLOTS;
   volatile int* tags = reinterpret_cast<volatile int*>(empty + GM_GRAM_MAX_SLOTS);
+  volatile int* cand = tags + GM_GRAM_MAX_SLOTS;   // producer scratch: (first row, rows) of up to 32 candidate groups
   const GramItem it = A.items[blockIdx.x];
   const GramDesc d = A.desc[it.desc];
   switch (d.tg) {
-    case 1: gram_cta<1>(A, it, d, ring, full, empty, tags); break;
-    case 2: gram_cta<2>(A, it, d, ring, full, empty, tags); break;
-    case 3: gram_cta<3>(A, it, d, ring, full, empty, tags); break;
-    case 4: gram_cta<4>(A, it, d, ring, full, empty, tags); break;
-    case 6: gram_cta<6>(A, it, d, ring, full, empty, tags); break;
-    default: gram_cta<8>(A, it, d, ring, full, empty, tags); break;
+    case 1: gram_cta<1>(A, it, d, ring, full, empty, tags, cand); break;
+    case 2: gram_cta<2>(A, it, d, ring, full, empty, tags, cand); break;
+    case 3: gram_cta<3>(A, it, d, ring, full, empty, tags, cand); break;
+    case 4: gram_cta<4>(A, it, d, ring, full, empty, tags, cand); break;
+    case 6: gram_cta<6>(A, it, d, ring, full, empty, tags, cand); break;
+    default: gram_cta<8>(A, it, d, ring, full, empty, tags, cand); break;
   }
 }
 
 // ================================================================================================ k_gram_sum
 // H[task][4][N][N] = sum of the partial Gram blocks of every (descriptor, team) in fixed order (deterministic).  One thread
 // per pair of adjacent columns; the partials of the teams of a descriptor are independent loads (latency overlapped).
+constexpr int GM_GRAM_SUM_MAXDESC = 48;
 struct GramSumArgs {
   int ndesc;
-  const GramDesc* desc;
+  GramDesc desc[GM_GRAM_SUM_MAXDESC];   // by value: read from the constant bank, no dependent global load per descriptor
   const double* hpart;
   long long hstride;
   int N;          // 8 * largest class
@@ -308,8 +313,8 @@ struct GramEvalArgs {
   int ntask, tasks_per_cta;
   const double* hsum;   // [ntask][4][N][N]
   int N;                // 8 * largest class
-  int ntile;            // column tiles that can be non-zero
-  int nk4;              // k4 steps over the rows of H that can be non-zero (<= 16, 4 nk4 <= nrows)
+  int ntile;            // column tiles that can be non-zero (template parameter of the launch)
+  int nk4;              // k4 steps whose p/q table rows exist (<= 2 ntile, 4 nk4 <= nrows); fragments beyond are zero
   int nbuf;             // shared-memory buffers for H (1 or 2)
   const double* T;      // p/q angle table of the bin, [2][nrows][GM_TROW]
   int nrows;
@@ -319,13 +324,14 @@ struct GramEvalArgs {
 
 constexpr int GM_GRAM_EVAL_THREADS = 384;
 constexpr int GM_GRAM_EVAL_SMEM_MAX = 220 * 1024;
-constexpr int GM_GRAM_NK4_MAX = 2 * GM_GRAM_MAX_TG;
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 
+template <int NTILE>
 __global__ void __launch_bounds__(GM_GRAM_EVAL_THREADS, 1) k_gram_eval(GramEvalArgs A) {
+  constexpr int NK4 = 2 * NTILE;   // compile-time trip counts: guarding DMMAs with run-time bounds only predicates them off
   extern __shared__ __align__(16) double Hs[];   // [nbuf][4][N][NP]
   const int N = A.N, NP = N + 4;
   const size_t buf_dbl = (size_t)4 * N * NP;
@@ -348,11 +354,11 @@ __global__ void __launch_bounds__(GM_GRAM_EVAL_THREADS, 1) k_gram_eval(GramEvalA
   if (t0 < t1) prefetch(t0, 0);
 
   // A fragments: lane (lr, lk) holds L[angle acol + lr][n = 4 ks + lk] for p (ap) and q (aq)
-  double ap[GM_GRAM_NK4_MAX], aq[GM_GRAM_NK4_MAX];
+  double ap[NK4], aq[NK4];
   {
     const double* Th = A.T + (size_t)half * A.nrows * GM_TROW + acol + lr;
 #pragma unroll
-    for (int ks = 0; ks < GM_GRAM_NK4_MAX; ++ks) {
+    for (int ks = 0; ks < NK4; ++ks) {
       ap[ks] = aq[ks] = 0.0;
       if (ks < A.nk4) {
         ap[ks] = Th[(size_t)(4 * ks + lk) * GM_TROW];
@@ -378,28 +384,25 @@ __global__ void __launch_bounds__(GM_GRAM_EVAL_THREADS, 1) k_gram_eval(GramEvalA
     for (int pair = 0; pair < 2; ++pair) {
       // pair 0: H1 (left p, right p) and H3 (left p, right q);  pair 1: H2 (left q, right q) and H4 (left p, right q)
       const int b0 = pair, b1 = pair + 2;
-      double acc0[GM_GRAM_MAX_TG][2], acc1[GM_GRAM_MAX_TG][2];
+      double acc0[NTILE][2], acc1[NTILE][2];
 #pragma unroll
-      for (int j = 0; j < GM_GRAM_MAX_TG; ++j) acc0[j][0] = acc0[j][1] = acc1[j][0] = acc1[j][1] = 0.0;
+      for (int j = 0; j < NTILE; ++j) acc0[j][0] = acc0[j][1] = acc1[j][0] = acc1[j][1] = 0.0;
       const double* H0 = Hb + (size_t)b0 * N * NP;
       const double* H1 = Hb + (size_t)b1 * N * NP;
 #pragma unroll
-      for (int ks = 0; ks < GM_GRAM_NK4_MAX; ++ks)
-        if (ks < A.nk4) {
-          const double a0 = pair == 0 ? ap[ks] : aq[ks];
-          const double a1 = ap[ks];
+      for (int ks = 0; ks < NK4; ++ks) {
+        const double a0 = pair == 0 ? ap[ks] : aq[ks];
+        const double a1 = ap[ks];
 #pragma unroll
-          for (int j = 0; j < GM_GRAM_MAX_TG; ++j)
-            if (j < A.ntile) {
-              dmma884(acc0[j][0], acc0[j][1], a0, H0[(size_t)4 * ks * NP + 8 * j]);
-              dmma884(acc1[j][0], acc1[j][1], a1, H1[(size_t)4 * ks * NP + 8 * j]);
-            }
+        for (int j = 0; j < NTILE; ++j) {
+          dmma884(acc0[j][0], acc0[j][1], a0, H0[(size_t)4 * ks * NP + 8 * j]);
+          dmma884(acc1[j][0], acc1[j][1], a1, H1[(size_t)4 * ks * NP + 8 * j]);
         }
+      }
       // right factors R[angle][c], c = 8 j + 2 lk (+1): held by lane (lr, c % 4) in fragment ks = c / 4
       double o0 = 0.0, o1 = 0.0;
 #pragma unroll
-      for (int j = 0; j < GM_GRAM_MAX_TG; ++j)
-        if (j < A.ntile) {
+      for (int j = 0; j < NTILE; ++j) {
           const double pe0 = __shfl_sync(0xffffffffu, ap[2 * j], src0), pe1 = __shfl_sync(0xffffffffu, ap[2 * j + 1], src0);
           const double po0 = __shfl_sync(0xffffffffu, ap[2 * j], src0 + 1), po1 = __shfl_sync(0xffffffffu, ap[2 * j + 1], src0 + 1);
           const double qe0 = __shfl_sync(0xffffffffu, aq[2 * j], src0), qe1 = __shfl_sync(0xffffffffu, aq[2 * j + 1], src0);
@@ -409,7 +412,7 @@ __global__ void __launch_bounds__(GM_GRAM_EVAL_THREADS, 1) k_gram_eval(GramEvalA
           const double r0a = pair == 0 ? pc : qc, r0b = pair == 0 ? pc1 : qc1;   // right factor of block b0
           o0 = fma(acc0[j][0], r0a, fma(acc0[j][1], r0b, o0));
           o1 = fma(acc1[j][0], qc, fma(acc1[j][1], qc1, o1));                     // blocks H3, H4: right factor q
-        }
+      }
       o0 += __shfl_xor_sync(0xffffffffu, o0, 1);
       o0 += __shfl_xor_sync(0xffffffffu, o0, 2);
       o1 += __shfl_xor_sync(0xffffffffu, o1, 1);
@@ -426,3 +429,4 @@ __global__ void __launch_bounds__(GM_GRAM_EVAL_THREADS, 1) k_gram_eval(GramEvalA
     if (A.nbuf == 1 && task + 1 < t1) prefetch(task + 1, 0);
   }
 }
+

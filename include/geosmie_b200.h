@@ -162,9 +162,9 @@ int gm_table_last_stats(gm_table_t t, double stats[8]);
 /* CUDA-event time (ms) of the contraction kernel launches of the last run (0 if timing disabled) */
 int gm_table_set_timing(gm_table_t t, int enable);
 int gm_table_last_kernel_ms(gm_table_t t, double* coeff_ms, double* contract_ms, double* finalize_ms);
-/* per-kernel split: ms[0..4] / n[0..4] = time and launches of k_coeff, k_contract, k_finalize, k_gram, k_gram_eval
- * (contract_ms above is the whole angular stage: k_contract + k_gram + k_gram_eval) */
-int gm_table_last_kernel_ms_ex(gm_table_t t, double ms[5], int32_t n[5]);
+/* per-kernel split: ms[0..4] / n[0..4] = time and event-bracketed launch groups of k_coeff, k_contract, k_finalize, k_gram,
+ * k_gram_sum + k_gram_eval (contract_ms above = k_contract + k_gram + k_gram_sum + k_gram_eval); entries 5..7 reserved */
+int gm_table_last_kernel_ms_ex(gm_table_t t, double ms[8], int32_t n[8]);
 
 /* ---- B4: generalized-spherical-function expansion ---------------------------------------------------------------------
  * Replaces one run of ./spher_expan.x per cell (src/gsf/spher_expan.f main :1-110, one_calc :120-180,
