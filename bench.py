@@ -13,8 +13,9 @@ One "step" = one pass of the hot path over that batch:
   e2e    the same through the host-buffer C ABI the table driver uses (gm_table_run_psd: per-cell refractive indices and
          size-distribution parameters in pinned host memory -> H2D -> kernels -> D2H of the reduced sums and GSF moments
          into pinned host memory, all inside the timed region);
-  roofline   FP64 tensor (DMMA) roofline of the dominant kernel k_contract, duration from CUDA events recorded around
-             each of its launches on the launching stream inside the timed steps;
+  roofline   FP64 tensor (DMMA) roofline of the dominant kernel (k_gram on optics_SU), duration from CUDA events recorded
+             around each of its launches on the launching stream inside the timed steps; the other kernels of the step
+             are listed under roofline.kernels with their own bounds;
   cpu_baseline   the CPU oracle port (oracle/mie_oracle.c, OpenMP) on a bounded sample of the same cells.
 With --gpus N (torchrun) every rank evaluates its own 2196-cell shard of an N-times larger grid (weak scaling) and the
 reduced sums are gathered to rank 0 with NCCL inside the timed region.
@@ -36,9 +37,10 @@ METRIC = "mie_particle_evals_per_sec"
 UNIT = "particle-evals/s"
 NANG = 371
 FP64_PEAK_TFLOPS = 37.1   # measured on this pool's B200 with tools/fp64_peak.cu (DMMA m8n8k4), profiles/r01_fp64_peak.json
-# dram__bytes_read.sum + dram__bytes_write.sum of k_contract per SU cell, from the `ncu --set full` capture
-# profiles/r01_contract_su_63cells.ncu-rep (83.54 MB + 13.58 MB over 63 dense cells)
-CONTRACT_DRAM_BYTES_PER_CELL = (83.544832e6 + 13.583616e6) / 63
+FP64_DFMA_PEAK_TFLOPS = 33.5   # same tool, plain DFMA (the pipe k_coeff runs on)
+# dram__bytes_read.sum + dram__bytes_write.sum of k_gram per SU cell, from the `ncu --set full` capture
+# profiles/r01h_gram_su_549cells.ncu-rep (726.42 MB + 164.86 MB over 549 dense cells)
+GRAM_DRAM_BYTES_PER_CELL = (726.423808e6 + 164.859136e6) / 549
 
 
 def build_su_plan():
@@ -48,14 +50,29 @@ def build_su_plan():
 
 
 def flop_model(nmax, nmx_sum, ncell_factor=1):
-    """Algorithmic FP64 flop of one pass.  `contract`: what the S+/S- formulation of k_contract needs -- 4 FMA per
-    (particle, n, angle) + 8 FMA per (particle, angle) for the weighted Mueller products;  `survey`: the
-    SURVEY 8d model F(p) = nmax (16 N_ang + 94) + 14 nmx + 22 N_ang (four separate complex dot products)."""
-    snm = float(np.sum(nmax)) * ncell_factor
-    npart = float(len(nmax)) * ncell_factor
-    contract = snm * 8.0 * NANG + npart * 16.0 * NANG
-    survey = snm * (16.0 * NANG + 94.0) + 14.0 * nmx_sum + npart * 22.0 * NANG
-    return contract, survey
+    """Algorithmic FP64 flop of one pass.
+    `contract`: the per-angle S+/S- formulation (k_contract): 4 FMA per (particle, n, angle) + 8 FMA per (particle, angle);
+    `survey`:   the SURVEY 8d model F(p) = nmax (16 N_ang + 94) + 14 nmx + 22 N_ang (the reference's four complex dots);
+    `gram`:     the Gram formulation (k_gram): four N x N blocks, K = 2 per particle -> 16 nmax^2 flop per particle, no
+                tile padding counted;
+    `gram_exec`: the DMMA flop k_gram actually issues (8-row tiles, classes 5 -> 6 and 7 -> 8 tiles, full symmetric blocks);
+    `coeff`:    14 nmx + 94 nmax per particle (recurrences, a_n, b_n, efficiencies)."""
+    nm = np.asarray(nmax, dtype=np.float64)
+    snm = float(nm.sum()) * ncell_factor
+    npart = float(len(nm)) * ncell_factor
+    ng = (len(nm) + 31) // 32
+    pad = np.zeros(ng * 32)
+    pad[:len(nm)] = nm
+    gm = pad.reshape(ng, 32).max(axis=1)
+    tg = np.ceil(gm / 8.0)
+    tg[tg == 5] = 6
+    tg[tg == 7] = 8
+    in_gram = gm <= 64
+    return {"contract": snm * 8.0 * NANG + npart * 16.0 * NANG,
+            "survey": snm * (16.0 * NANG + 94.0) + 14.0 * nmx_sum + npart * 22.0 * NANG,
+            "gram": 16.0 * float((nm[np.repeat(in_gram, 32)[:len(nm)]] ** 2).sum()) * ncell_factor,
+            "gram_exec": 512.0 * float((4.0 * tg[in_gram] ** 2 * 16.0).sum()) * ncell_factor,
+            "coeff": 14.0 * nmx_sum + 94.0 * snm}
 
 
 class ClockSampler(threading.Thread):
@@ -276,8 +293,31 @@ def main():
     total_evals = float(ncell) * nx * world
     value = total_evals / (ms_dev * 1e-3)
     e2e = total_evals / (ms_e2e * 1e-3)
-    contract_flop, survey_flop = flop_model(plan.nmax, stats["sum_nmx"], ncell)
-    ach = contract_flop / (kms["contract"] * 1e-3) / 1e12 if kms["contract"] > 0 else None
+    fl = flop_model(plan.nmax, stats["sum_nmx"], ncell)
+
+    def tf(flop, ms):
+        return flop / (ms * 1e-3) / 1e12 if ms and ms > 0 else None
+
+    kernels = {
+        "k_gram": {"bound": "tensor", "ms": kms["k_gram"], "achieved": tf(fl["gram"], kms["k_gram"]), "peak": FP64_PEAK_TFLOPS,
+                   "unit": "TFLOP/s", "executed": tf(fl["gram_exec"], kms["k_gram"]),
+                   "note": "achieved = 16 nmax^2 flop per particle (no tile padding); executed = DMMA flop actually issued"},
+        "k_coeff": {"bound": "fp64 vector pipe (latency-bound recurrences)", "ms": kms["k_coeff"],
+                    "achieved": tf(fl["coeff"], kms["k_coeff"]), "peak": FP64_DFMA_PEAK_TFLOPS, "unit": "TFLOP/s"},
+        "k_gram_sum+k_gram_eval": {"bound": "tensor", "ms": kms["k_gram_sum_eval"],
+                                   "achieved": tf(8.0 * NANG * float(plan.nmax.max()) ** 2 * ncell, kms["k_gram_sum_eval"]),
+                                   "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+                                   "note": "4 quadratic forms of size max(nmax) at 371 angles per cell"},
+        "k_contract": {"bound": "tensor", "ms": kms["k_contract"], "achieved": None, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+                       "note": "per-angle contraction of groups with nmax > 64: none in optics_SU"},
+        "k_finalize": {"bound": "hbm", "ms": kms["k_finalize"]},
+    }
+    for k in kernels.values():
+        if k.get("achieved") and k.get("peak"):
+            k["frac"] = k["achieved"] / k["peak"]
+    dom = max(("k_gram", "k_coeff", "k_gram_sum+k_gram_eval", "k_contract"), key=lambda k: kernels[k]["ms"] or 0.0)
+    D = kernels[dom]
+    ach = D.get("achieved")
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -285,23 +325,31 @@ def main():
         "data": "su.json parameters; OPAC sulfate + HITRAN water refractive indices (tests/golden/hostlogic.npz)",
         "config": {"workload": "optics_SU dense table build: 1 bin x 4459 sizes x 61 lambda x 36 RH = 2196 cells, 371 angles, "
                                "then 129 GSF moments x 6 per cell", "cells_per_gpu": ncell, "nx": nx, "nang": NANG,
-                   "l2_policy": "inputs larger than L2 per step: 78 MB weights + 2.9 GB coefficient stream re-written every step",
+                   "l2_policy": "inputs larger than L2 per step: 78 MB weights + 2.9 GB coefficient stream + 0.66 GB partial Gram blocks re-written every step",
                    "parallelism": "cells sharded, %d rank(s), NCCL gather to rank 0" % world},
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(mz_psd.nbytes * 2 + psd_par.nbytes + psd_frac.nbytes),
                 "api": "gm_table_run_psd with the fused GSF stage (host buffers: per-cell m and PSD parameters in, reduced sums and GSF moments out)",
                 "d2h_bytes_per_step": int(scal_h.numel() * 8 + phase_h.numel() * 8 + coef_h.numel() * 8)},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "k_contract<false> (FP64 DMMA m8n8k4)", "achieved": ach, "peak": FP64_PEAK_TFLOPS,
-                     "unit": "TFLOP/s", "frac": (ach / FP64_PEAK_TFLOPS) if ach else None,
-                     "traffic": CONTRACT_DRAM_BYTES_PER_CELL * ncell,
-                     "traffic_note": "DRAM bytes of the k_contract launches of one step, scaled per cell from the ncu capture in "
-                                     "profiles/ (algorithmic: 32 B x sum(nmax) coefficient stream = %.2e B)" % (32.0 * float(np.sum(plan.nmax)) * ncell),
-                     "peak_source": "measured on this pool: tools/fp64_peak.cu DMMA burst 37.1 TFLOP/s (MEASURED_PEAKS.json has "
-                                    "no FP64 entry; nominal 37 TFLOP/s)",
-                     "flop_per_launch_set": contract_flop, "kernel_ms_per_step": kms,
-                     "step_tflops_survey_flop_model_per_gpu": survey_flop / (ms_dev * 1e-3) / 1e12,
-                     "kernel_share_of_step": kms["contract"] / ms_dev if ms_dev else None},
+        "roofline": {"bound": "tensor" if D["bound"] == "tensor" else "fp64",
+                     "kernel": (dom + " (FP64 DMMA m8n8k4)") if D["bound"] == "tensor" else dom,
+                     "achieved": ach, "peak": D.get("peak"), "unit": "TFLOP/s", "frac": D.get("frac"),
+                     "executed_frac": (D["executed"] / D["peak"]) if D.get("executed") else None,
+                     "traffic": GRAM_DRAM_BYTES_PER_CELL * ncell if dom == "k_gram" else None,
+                     "traffic_note": "DRAM bytes of the k_gram launch of one step, scaled per cell from the ncu capture in "
+                                     "profiles/ (algorithmic: 32 B x sum(nmax) coefficient stream = %.2e B read + partial Gram "
+                                     "blocks written)" % (32.0 * float(np.sum(plan.nmax)) * ncell),
+                     "peak_source": "measured on this pool: tools/fp64_peak.cu DMMA burst 37.1 TFLOP/s, DFMA 33.5 TFLOP/s "
+                                    "(MEASURED_PEAKS.json has no FP64 entry; nominal 37 TFLOP/s)",
+                     "flop_per_launch_set": fl["gram"] if dom == "k_gram" else None,
+                     "kernel_ms_per_step": kms, "kernels": kernels,
+                     "step_tflops_survey_flop_model_per_gpu": fl["survey"] / (ms_dev * 1e-3) / 1e12,
+                     "step_tflops_per_angle_model_per_gpu": fl["contract"] / (ms_dev * 1e-3) / 1e12,
+                     "model_note": "TFLOP/s the reference formulation (SURVEY 8d) / the per-angle S+/S- formulation would need to "
+                                   "do this step in the same time; both exceed the 37.1 TFLOP/s peak because the Gram form needs "
+                                   "~9x fewer flop when nmax << N_ang",
+                     "kernel_share_of_step": (D["ms"] / ms_dev) if ms_dev else None},
         "clocks": clocks,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -60,6 +60,9 @@ extern "C" int gm_destroy(gm_handle_t h) {
   if (!h) return GM_OK;
   cudaSetDevice(h->device);
   for (auto& b : h->ws) b.release();
+  for (DevBuf* b : {&h->scratch_coef, &h->scratch_gact, &h->scratch_scal_part, &h->scratch_part, &h->scratch_g_hpart, &h->scratch_g_hsum,
+                    &h->scratch_wphase, &h->scratch_wscal})
+    b->release();
   h->gsf_nodes.release();
   h->gsf_table.release();
   delete h;
@@ -317,7 +320,7 @@ struct gm_table_s {
   std::vector<double> hx;
   std::vector<int32_t> hnmax;
   DevBuf T, cost, dr, psd_par, psd_frac;
-  DevBuf g_list, g_skip, g_desc, g_items, g_hpart, g_hsum;   // Gram path (gm_gram.cuh)
+  DevBuf g_list, g_skip, g_desc, g_items;   // Gram path (gm_gram.cuh)
   DevBuf c_ab, c_scratch, c_soff, c_aboff, c_ratio;   // coated-sphere table path
   // fused GSF stage (gm_table_set_gsf): moments of every finished batch are expanded and downloaded behind the kernels
   std::vector<double> gsf_ang;
@@ -329,7 +332,7 @@ struct gm_table_s {
   bool have_dr = false;
   bool psd_separate = false;
   // per-run buffers
-  DevBuf coef, gact, scal_part, part, chunk_start, mz, mrel, wphase, wscal, out_scal, out_phase, stats, q, s12;
+  DevBuf chunk_start, mz, mrel, out_scal, out_phase, stats, q, s12;   // the large per-run scratch lives in the handle (shared by its tables)
   double last_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int timing = 0;
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // host-buffer calls: copies pipelined against the kernels
@@ -387,8 +390,7 @@ extern "C" int gm_table_destroy(gm_table_t t) {
   if (!t) return GM_OK;
   cudaSetDevice(t->h->device);
   t->D.release();
-  for (DevBuf* b : {&t->g_hsum, &t->g_list, &t->g_skip, &t->g_desc, &t->g_items, &t->g_hpart, &t->gsf_coef, &t->gsf_cnorm, &t->c_ab, &t->c_scratch, &t->c_soff, &t->c_aboff, &t->c_ratio, &t->dr, &t->psd_par, &t->psd_frac, &t->T, &t->cost, &t->coef, &t->gact, &t->scal_part, &t->part, &t->chunk_start, &t->mz, &t->mrel, &t->wphase,
-                    &t->wscal, &t->out_scal, &t->out_phase, &t->stats, &t->q, &t->s12})
+  for (DevBuf* b : {&t->g_list, &t->g_skip, &t->g_desc, &t->g_items, &t->gsf_coef, &t->gsf_cnorm, &t->c_ab, &t->c_scratch, &t->c_soff, &t->c_aboff, &t->c_ratio, &t->dr, &t->psd_par, &t->psd_frac, &t->T, &t->cost, &t->chunk_start, &t->mz, &t->mrel, &t->out_scal, &t->out_phase, &t->stats, &t->q, &t->s12})
     b->release();
   for (auto& e : t->evpool) cudaEventDestroy(e);
   for (auto& e : t->io_events) cudaEventDestroy(e);
@@ -613,15 +615,15 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
     long long hmax = 0;
     for (auto& P : plans) hmax = std::max(hmax, P.hstride * P.nt);
     if ((rc = t->g_desc.ensure(sizeof(GramDesc) * all_desc.size())) || (rc = t->g_items.ensure(sizeof(GramItem) * all_items.size())) ||
-        (rc = t->g_hpart.ensure(sizeof(double) * (size_t)hmax)) ||
-        (rc = t->g_hsum.ensure(sizeof(double) * (size_t)tb * 4 * 64 * G.gram_tgmax * G.gram_tgmax)))
+        (rc = t->h->scratch_g_hpart.ensure(sizeof(double) * (size_t)hmax)) ||
+        (rc = t->h->scratch_g_hsum.ensure(sizeof(double) * (size_t)tb * 4 * 64 * G.gram_tgmax * G.gram_tgmax)))
       return rc;
     GM_CUDA_TRY(cudaMemcpyAsync(t->g_desc.p, all_desc.data(), sizeof(GramDesc) * all_desc.size(), cudaMemcpyHostToDevice, st));
     GM_CUDA_TRY(cudaMemcpyAsync(t->g_items.p, all_items.data(), sizeof(GramItem) * all_items.size(), cudaMemcpyHostToDevice, st));
   }
-  if ((rc = t->coef.ensure(per_task_bytes * tb)) || (rc = t->gact.ensure((size_t)tb * G.ngroup)) ||
-      (rc = t->scal_part.ensure(sizeof(double) * (size_t)tb * nmode * G.ngroup * GM_NSCAL)) ||
-      (rc = t->part.ensure(sizeof(double) * (size_t)tb * nchunk_total * 4 * GM_NANG_PAD)) ||
+  if ((rc = t->h->scratch_coef.ensure(per_task_bytes * tb)) || (rc = t->h->scratch_gact.ensure((size_t)tb * G.ngroup)) ||
+      (rc = t->h->scratch_scal_part.ensure(sizeof(double) * (size_t)tb * nmode * G.ngroup * GM_NSCAL)) ||
+      (rc = t->h->scratch_part.ensure(sizeof(double) * (size_t)tb * nchunk_total * 4 * GM_NANG_PAD)) ||
       (rc = t->chunk_start.ensure(sizeof(int) * (nchunk + 1))) || (rc = t->stats.ensure(sizeof(unsigned long long) * 8)))
     return rc;
   if (t->gsf_ng > 0 && !per_particle) {
@@ -683,10 +685,10 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
     A.scale_sqrtw = per_particle ? 0 : 1;
     A.grow = t->D.grow.as<int>();
     A.gk4 = t->D.gk4.as<int>();
-    A.coef = t->coef.as<double>();
+    A.coef = t->h->scratch_coef.as<double>();
     A.task_stride = task_stride;
-    A.gact = t->gact.as<unsigned char>();
-    A.scal_part = t->scal_part.as<double>();
+    A.gact = t->h->scratch_gact.as<unsigned char>();
+    A.scal_part = t->h->scratch_scal_part.as<double>();
     A.q = d_q ? d_q + (size_t)t0 * G.nx * 6 : nullptr;
     A.stats = t->stats.as<unsigned long long>();
     const GramPlan* P = nullptr;
@@ -717,14 +719,14 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
     C.nchunk = nchunk;
     C.nrows = t->nrows;
     C.T = t->T.as<double>();
-    C.coef = t->coef.as<double>();
+    C.coef = t->h->scratch_coef.as<double>();
     C.task_stride = task_stride;
     C.grow = t->D.grow.as<int>();
     C.gk4 = t->D.gk4.as<int>();
-    C.gact = t->gact.as<unsigned char>();
+    C.gact = t->h->scratch_gact.as<unsigned char>();
     C.gskip = use_gram ? t->g_skip.as<unsigned char>() : nullptr;
     C.chunk_start = t->chunk_start.as<int>();
-    C.part = t->part.as<double>();
+    C.part = t->h->scratch_part.as<double>();
     C.nchunk_total = nchunk_total;
     C.nx = G.nx;
     C.nang = t->nang;
@@ -747,10 +749,10 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
       GA.glist = t->g_list.as<int>();
       GA.grow = t->D.grow.as<int>();
       GA.gk4 = t->D.gk4.as<int>();
-      GA.gact = t->gact.as<unsigned char>();
-      GA.coef = t->coef.as<double>();
+      GA.gact = t->h->scratch_gact.as<unsigned char>();
+      GA.coef = t->h->scratch_coef.as<double>();
       GA.task_stride = task_stride;
-      GA.hpart = t->g_hpart.as<double>();
+      GA.hpart = t->h->scratch_g_hpart.as<double>();
       GA.hstride = P->hstride;
       if (P->nitem > 0) {
         if ((rc = ev_mark(t, 3))) return rc;
@@ -767,7 +769,7 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
       SA.hpart = GA.hpart;
       SA.hstride = P->hstride;
       SA.N = N;
-      SA.hsum = t->g_hsum.as<double>();
+      SA.hsum = t->h->scratch_g_hsum.as<double>();
       GramEvalArgs EA;
       memset(&EA, 0, sizeof(EA));
       EA.ntask = nt;
@@ -780,7 +782,7 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
       EA.nbuf = 2 * hbytes <= GM_GRAM_EVAL_SMEM_MAX ? 2 : 1;
       EA.T = t->T.as<double>();
       EA.nrows = t->nrows;
-      EA.part = t->part.as<double>();
+      EA.part = t->h->scratch_part.as<double>();
       EA.nchunk = nchunk_total;
       EA.chunk = nchunk;
       if ((rc = ev_mark(t, 4))) return rc;
@@ -802,7 +804,7 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
     }
     if (!per_particle) {
       if ((rc = ev_mark(t, 2))) return rc;
-      k_finalize<<<nt, GM_NANG_PAD, 0, st>>>(nchunk_total, G.ngroup, nmode, t->nang, t->part.as<double>(), t->scal_part.as<double>(),
+      k_finalize<<<nt, GM_NANG_PAD, 0, st>>>(nchunk_total, G.ngroup, nmode, t->nang, t->h->scratch_part.as<double>(), t->h->scratch_scal_part.as<double>(),
                                              d_out_phase + (size_t)t0 * 4 * t->nang, d_out_scal + (size_t)t0 * nmode * GM_NSCAL);
       GM_LAUNCH_CHECK(h);
       if ((rc = ev_mark(t, 2))) return rc;
@@ -867,15 +869,15 @@ extern "C" int gm_table_run(gm_table_t t, int ntask, const double* mz, const dou
   int rc;
   const size_t nw = (size_t)ntask * t->nx;
   if ((rc = t->mz.ensure(sizeof(double2) * ntask)) || (rc = t->mrel.ensure(sizeof(double2) * ntask)) ||
-      (rc = t->wphase.ensure(sizeof(double) * nw)) || (rc = t->out_scal.ensure(sizeof(double) * (size_t)ntask * nmode * GM_NSCAL)) ||
+      (rc = t->h->scratch_wphase.ensure(sizeof(double) * nw)) || (rc = t->out_scal.ensure(sizeof(double) * (size_t)ntask * nmode * GM_NSCAL)) ||
       (rc = t->out_phase.ensure(sizeof(double) * (size_t)ntask * 4 * t->nang)))
     return rc;
-  if (w_scal && (rc = t->wscal.ensure(sizeof(double) * nw * nmode))) return rc;
+  if (w_scal && (rc = t->h->scratch_wscal.ensure(sizeof(double) * nw * nmode))) return rc;
   GM_CUDA_TRY(cudaMemcpyAsync(t->mz.p, mz, sizeof(double2) * ntask, cudaMemcpyHostToDevice, st));
   GM_CUDA_TRY(cudaMemcpyAsync(t->mrel.p, mrel, sizeof(double2) * ntask, cudaMemcpyHostToDevice, st));
   HostIO hio = {w_phase, w_scal, out_scal, out_phase};
-  rc = table_run_core(t, ntask, t->mz.as<double>(), t->mrel.as<double>(), nmode, t->wphase.as<double>(),
-                      w_scal ? t->wscal.as<double>() : nullptr, flags, t->out_scal.as<double>(), t->out_phase.as<double>(), nullptr,
+  rc = table_run_core(t, ntask, t->mz.as<double>(), t->mrel.as<double>(), nmode, t->h->scratch_wphase.as<double>(),
+                      w_scal ? t->h->scratch_wscal.as<double>() : nullptr, flags, t->out_scal.as<double>(), t->out_phase.as<double>(), nullptr,
                       nullptr, false, &hio);
   if (rc) return rc;
   return fetch_stats(t);
@@ -907,17 +909,17 @@ extern "C" int gm_table_run_coated(gm_table_t t, int ntask, const double* m1, co
   }
   const size_t nw = (size_t)ntask * t->nx;
   if ((rc = t->mz.ensure(sizeof(double2) * ntask)) || (rc = t->mrel.ensure(sizeof(double2) * ntask)) ||
-      (rc = t->c_ratio.ensure(sizeof(double) * ntask)) || (rc = t->wphase.ensure(sizeof(double) * nw)) ||
+      (rc = t->c_ratio.ensure(sizeof(double) * ntask)) || (rc = t->h->scratch_wphase.ensure(sizeof(double) * nw)) ||
       (rc = t->out_scal.ensure(sizeof(double) * (size_t)ntask * nmode * GM_NSCAL)) ||
       (rc = t->out_phase.ensure(sizeof(double) * (size_t)ntask * 4 * t->nang)))
     return rc;
-  if (w_scal && (rc = t->wscal.ensure(sizeof(double) * nw * nmode))) return rc;
+  if (w_scal && (rc = t->h->scratch_wscal.ensure(sizeof(double) * nw * nmode))) return rc;
   GM_CUDA_TRY(cudaMemcpyAsync(t->mz.p, m1, sizeof(double2) * ntask, cudaMemcpyHostToDevice, st));
   GM_CUDA_TRY(cudaMemcpyAsync(t->mrel.p, m2, sizeof(double2) * ntask, cudaMemcpyHostToDevice, st));
   GM_CUDA_TRY(cudaMemcpyAsync(t->c_ratio.p, core_ratio, sizeof(double) * ntask, cudaMemcpyHostToDevice, st));
   HostIO hio = {w_phase, w_scal, out_scal, out_phase};
-  rc = table_run_core(t, ntask, t->mz.as<double>(), t->mrel.as<double>(), nmode, t->wphase.as<double>(),
-                      w_scal ? t->wscal.as<double>() : nullptr, flags, t->out_scal.as<double>(), t->out_phase.as<double>(), nullptr,
+  rc = table_run_core(t, ntask, t->mz.as<double>(), t->mrel.as<double>(), nmode, t->h->scratch_wphase.as<double>(),
+                      w_scal ? t->h->scratch_wscal.as<double>() : nullptr, flags, t->out_scal.as<double>(), t->out_phase.as<double>(), nullptr,
                       nullptr, false, &hio, t->c_ratio.as<double>());
   if (rc) return rc;
   return fetch_stats(t);
@@ -973,23 +975,23 @@ extern "C" int gm_table_run_psd(gm_table_t t, int ntask, const double* mz, const
   bool separate = nmode > 1;
   for (int i = 0; i < ntask * nmode && !separate; ++i) separate = frac[i] != 1.0;
   if ((rc = t->mz.ensure(sizeof(double2) * ntask)) || (rc = t->mrel.ensure(sizeof(double2) * ntask)) ||
-      (rc = t->wphase.ensure(sizeof(double) * nw)) || (rc = t->out_scal.ensure(sizeof(double) * (size_t)ntask * nmode * GM_NSCAL)) ||
+      (rc = t->h->scratch_wphase.ensure(sizeof(double) * nw)) || (rc = t->out_scal.ensure(sizeof(double) * (size_t)ntask * nmode * GM_NSCAL)) ||
       (rc = t->out_phase.ensure(sizeof(double) * (size_t)ntask * 4 * t->nang)) ||
       (rc = t->psd_par.ensure(sizeof(double) * (size_t)ntask * nmode * GM_PSD_NPAR)) ||
       (rc = t->psd_frac.ensure(sizeof(double) * (size_t)ntask * nmode)))
     return rc;
-  if (separate && (rc = t->wscal.ensure(sizeof(double) * nw * nmode))) return rc;
+  if (separate && (rc = t->h->scratch_wscal.ensure(sizeof(double) * nw * nmode))) return rc;
   GM_CUDA_TRY(cudaMemcpyAsync(t->mz.p, mz, sizeof(double2) * ntask, cudaMemcpyHostToDevice, st));
   GM_CUDA_TRY(cudaMemcpyAsync(t->mrel.p, mrel, sizeof(double2) * ntask, cudaMemcpyHostToDevice, st));
   GM_CUDA_TRY(cudaMemcpyAsync(t->psd_par.p, psd_params, sizeof(double) * (size_t)ntask * nmode * GM_PSD_NPAR, cudaMemcpyHostToDevice, st));
   GM_CUDA_TRY(cudaMemcpyAsync(t->psd_frac.p, frac, sizeof(double) * (size_t)ntask * nmode, cudaMemcpyHostToDevice, st));
   k_psd<<<ntask, 256, 0, st>>>(t->nx, nmode, psd_kind, t->D.x.as<double>(), t->dr.as<double>(), t->psd_par.as<double>(),
-                               t->psd_frac.as<double>(), t->wscal.as<double>(), t->wphase.as<double>(), separate ? 1 : 0);
+                               t->psd_frac.as<double>(), t->h->scratch_wscal.as<double>(), t->h->scratch_wphase.as<double>(), separate ? 1 : 0);
   GM_LAUNCH_CHECK(h);
   t->psd_separate = separate;
   HostIO hio = {nullptr, nullptr, out_scal, out_phase};   // results are downloaded batch by batch behind the kernels
-  rc = table_run_core(t, ntask, t->mz.as<double>(), t->mrel.as<double>(), nmode, t->wphase.as<double>(),
-                      separate ? t->wscal.as<double>() : nullptr, flags, t->out_scal.as<double>(), t->out_phase.as<double>(), nullptr,
+  rc = table_run_core(t, ntask, t->mz.as<double>(), t->mrel.as<double>(), nmode, t->h->scratch_wphase.as<double>(),
+                      separate ? t->h->scratch_wscal.as<double>() : nullptr, flags, t->out_scal.as<double>(), t->out_phase.as<double>(), nullptr,
                       nullptr, false, &hio);
   if (rc) return rc;
   return fetch_stats(t);
@@ -998,7 +1000,7 @@ extern "C" int gm_table_run_psd(gm_table_t t, int ntask, const double* mz, const
 extern "C" int gm_table_get_weights(gm_table_t t, int ntask, int nmode, double* w) {
   GM_REQUIRE(t && w, "NULL argument");
   GM_CUDA_TRY(cudaSetDevice(t->h->device));
-  const void* src = t->psd_separate ? t->wscal.p : t->wphase.p;
+  const void* src = t->psd_separate ? t->h->scratch_wscal.p : t->h->scratch_wphase.p;
   GM_REQUIRE(src != nullptr, "no weights have been generated");
   GM_CUDA_TRY(cudaMemcpyAsync(w, src, sizeof(double) * (size_t)ntask * nmode * t->nx, cudaMemcpyDeviceToHost, t->h->stream));
   GM_CUDA_TRY(cudaStreamSynchronize(t->h->stream));
@@ -1022,15 +1024,15 @@ extern "C" int gm_table_particles(gm_table_t t, int ntask, const double* mz, con
   int rc;
   const size_t np = (size_t)ntask * t->nx;
   if ((rc = t->mz.ensure(sizeof(double2) * ntask)) || (rc = t->mrel.ensure(sizeof(double2) * ntask)) ||
-      (rc = t->q.ensure(sizeof(double) * 6 * np)) || (rc = t->wphase.ensure(sizeof(double) * np)))
+      (rc = t->q.ensure(sizeof(double) * 6 * np)) || (rc = t->h->scratch_wphase.ensure(sizeof(double) * np)))
     return rc;
   if (s12 && (rc = t->s12.ensure(sizeof(double) * 4 * np * t->nang))) return rc;
   GM_CUDA_TRY(cudaMemcpyAsync(t->mz.p, mz, sizeof(double2) * ntask, cudaMemcpyHostToDevice, st));
   GM_CUDA_TRY(cudaMemcpyAsync(t->mrel.p, mrel, sizeof(double2) * ntask, cudaMemcpyHostToDevice, st));
-  GM_CUDA_TRY(cudaMemsetAsync(t->wphase.p, 0, sizeof(double) * np, st));
+  GM_CUDA_TRY(cudaMemsetAsync(t->h->scratch_wphase.p, 0, sizeof(double) * np, st));
   if ((rc = t->out_scal.ensure(sizeof(double) * (size_t)ntask * GM_NSCAL)) || (rc = t->out_phase.ensure(sizeof(double) * (size_t)ntask * 4 * t->nang)))
     return rc;
-  rc = table_run_core(t, ntask, t->mz.as<double>(), t->mrel.as<double>(), 1, t->wphase.as<double>(), nullptr, 0,
+  rc = table_run_core(t, ntask, t->mz.as<double>(), t->mrel.as<double>(), 1, t->h->scratch_wphase.as<double>(), nullptr, 0,
                       t->out_scal.as<double>(), t->out_phase.as<double>(), t->q.as<double>(), s12 ? t->s12.as<double>() : nullptr,
                       s12 != nullptr);
   if (rc) return rc;

@@ -236,26 +236,28 @@ __global__ void __launch_bounds__(128, GM_COEFF_MINB) k_coeff(CoeffArgs A) {
   }
 
   // ---- phase 1: orders above every particle of the group: only the logarithmic-derivative recurrence
-  // mie_coeffs.py:119-121, D_n = r - 1/(D_{n+1} + r), r = (n+1)/z, started from D_{nmx} = 0
+  // mie_coeffs.py:119-121, D_n = r - 1/(D_{n+1} + r), r = (n+1)/z, started from D_{nmx} = 0.  It is carried in the
+  // denominator t_n = D_{n+1} + (n+1)/z:  D_n = (n+1)/z - 1/t_n  and  t_{n-1} = D_n + n/z = (2n+1)/z - 1/t_n, i.e. one
+  // complex reciprocal and two FMAs per order (D_n itself is only formed for the orders that emit coefficients).
   int nstart = J - 1;
   const int nemit = TABLE ? rows : __reduce_max_sync(0xffffffffu, act ? nm : 0);
   if (nemit > nstart) nstart = nemit;
   int n = nstart;
-  for (; n > nemit; --n) {
+  double2 tt = make_double2((double)nmx * zinv.x, (double)nmx * zinv.y);   // t_{nmx-1}: D_{nmx} = 0
+  double f2 = (double)(2 * nstart + 1);                                     // 2n + 1, warp-uniform, exact
+  for (; n > nemit; --n, f2 -= 2.0) {
     if (n < nmx) {
-      const double f = (double)(n + 1);
-      const double2 r = make_double2(f * zinv.x, f * zinv.y);
-      const double2 ti = crcp(make_double2(D.x + r.x, D.y + r.y));
-      D = make_double2(r.x - ti.x, r.y - ti.y);
+      const double2 ti = crcp(tt);
+      tt = make_double2(fma(f2, zinv.x, -ti.x), fma(f2, zinv.y, -ti.y));
     }
   }
   // ---- phase 2: orders that emit coefficients
-  for (; n >= 1; --n) {
+  for (; n >= 1; --n, f2 -= 2.0) {
     if (n < nmx) {
-      const double f = (double)(n + 1);
-      const double2 r = make_double2(f * zinv.x, f * zinv.y);
-      const double2 ti = crcp(make_double2(D.x + r.x, D.y + r.y));
-      D = make_double2(r.x - ti.x, r.y - ti.y);
+      const double2 ti = crcp(tt);
+      const double f1 = 0.5 * f2 + 0.5;                                     // n + 1
+      D = make_double2(fma(f1, zinv.x, -ti.x), fma(f1, zinv.y, -ti.y));
+      tt = make_double2(fma(f2, zinv.x, -ti.x), fma(f2, zinv.y, -ti.y));
     }
     double2 cp = make_double2(0.0, 0.0), cm = make_double2(0.0, 0.0);
     if (act && n <= nm) {
