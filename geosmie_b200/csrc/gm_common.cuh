@@ -120,6 +120,36 @@ __device__ __forceinline__ double2 cdiv(double2 a, double2 b) {
   double inv = fast_rcp(fma(b.x, b.x, b.y * b.y));
   return make_double2(fma(a.x, b.x, a.y * b.y) * inv, fma(a.y, b.x, -a.x * b.y) * inv);
 }
+// Sums 16 per-lane values over the warp with 16 shuffles instead of 80: each round halves the number of values a lane
+// carries (the half it gives away goes to its partner), so after four rounds lane L holds the sum over 16 lanes of value
+// idx(L) = bits 4,3,2,1 of L, and the last round adds the two halves.  Fixed order: deterministic.  Returns the total of
+// value warp_reduce16_index(lane) in every lane.
+__device__ __forceinline__ int warp_reduce16_index(int lane) {
+  return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+}
+__device__ __forceinline__ double warp_reduce16(const double (&v)[16], int lane) {
+  double a[8], b[4], c[2];
+  const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4, u2 = lane & 2;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const double keep = u16 ? v[8 + i] : v[i], give = u16 ? v[i] : v[8 + i];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, give, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double keep = u8 ? a[4 + i] : a[i], give = u8 ? a[i] : a[4 + i];
+    b[i] = keep + __shfl_xor_sync(0xffffffffu, give, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const double keep = u4 ? b[2 + i] : b[i], give = u4 ? b[i] : b[2 + i];
+    c[i] = keep + __shfl_xor_sync(0xffffffffu, give, 4);
+  }
+  const double keep = u2 ? c[1] : c[0], give = u2 ? c[0] : c[1];
+  double d = keep + __shfl_xor_sync(0xffffffffu, give, 2);
+  d += __shfl_xor_sync(0xffffffffu, d, 1);
+  return d;
+}
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

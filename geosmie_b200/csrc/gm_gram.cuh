@@ -301,6 +301,12 @@ __global__ void __launch_bounds__(256) k_gram_sum(GramSumArgs A) {
       }
     }
   }
+  if (b < 2) {
+    // H1, H2 are symmetric: hand k_gram_eval the upper triangle with doubled off-diagonal (p^T U p = p^T H p), so that it can
+    // skip the tiles below the diagonal
+    s.x = c > n ? 2.0 * s.x : (c == n ? s.x : 0.0);
+    s.y = c + 1 > n ? 2.0 * s.y : (c + 1 == n ? s.y : 0.0);
+  }
   *reinterpret_cast<double2*>(A.hsum + (((size_t)task * 4 + b) * N + n) * N + c) = s;
 }
 
@@ -395,7 +401,8 @@ __global__ void __launch_bounds__(GM_GRAM_EVAL_THREADS, 1) k_gram_eval(GramEvalA
         const double a1 = ap[ks];
 #pragma unroll
         for (int j = 0; j < NTILE; ++j) {
-          dmma884(acc0[j][0], acc0[j][1], a0, H0[(size_t)4 * ks * NP + 8 * j]);
+          if (8 * j + 7 >= 4 * ks)   // block b0 (H1 / H2) is upper triangular (k_gram_sum): tiles below the diagonal are zero
+            dmma884(acc0[j][0], acc0[j][1], a0, H0[(size_t)4 * ks * NP + 8 * j]);
           dmma884(acc1[j][0], acc1[j][1], a1, H1[(size_t)4 * ks * NP + 8 * j]);
         }
       }

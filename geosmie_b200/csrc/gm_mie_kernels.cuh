@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(128, GM_COEFF_MINB) k_coeff(CoeffArgs A) {
   }
   const bool act = valid && (MODE == 1 || A.dense || any);
   const double2 z = make_double2(mzv.x * xi, mzv.y * xi);                     // mie_coeffs.py:96
-  const int nmx = (act && MODE != 2) ? (int)rint(fmax((double)nm, hypot(z.x, z.y)) + 16.0) : 0;  // mie_coeffs.py:101
+  const int nmx = (act && MODE != 2) ? (int)rint(fmax((double)nm, sqrt(fma(z.x, z.x, z.y * z.y))) + 16.0) : 0;  // mie_coeffs.py:101
   const int J = __reduce_max_sync(0xffffffffu, nmx);
   int rows = 0;
   if (TABLE) {
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(128, GM_COEFF_MINB) k_coeff(CoeffArgs A) {
     double2 cp = make_double2(0.0, 0.0), cm = make_double2(0.0, 0.0);
     if (act && n <= nm) {
       double2 an, bn;
-      const double dn = (double)n;
+      const double dn = 0.5 * f2 - 0.5;   // n (f2 = 2n + 1 is carried as a double: no int -> double conversion per order)
       if (MODE == 2) {
         const double4 v = ab_in[abo + n - 1];
         an = make_double2(v.x, v.y);
@@ -319,15 +319,21 @@ __global__ void __launch_bounds__(128, GM_COEFF_MINB) k_coeff(CoeffArgs A) {
     }
   }
   // mie_props.py:44-68
+  // (divisions by y^2 and qsca as multiplications by reciprocals: <= 2 ulp from the reference's quotients)
   double qv[6] = {0, 0, 0, 0, 0, 0};
+  double gq = 0.0;   // asy * qsca
   if (act) {
-    const double y2 = xi * xi;
-    qv[0] = 2.0 * sext / y2;
-    qv[1] = 2.0 * ssca / y2;
+    const double iy2 = xinv * xinv;
+    qv[0] = 2.0 * sext * iy2;
+    qv[1] = 2.0 * ssca * iy2;
     qv[2] = qv[0] - qv[1];
-    qv[3] = (qbr * qbr + qbi * qbi) / y2;
-    qv[4] = 4.0 / y2 * sasy / qv[1];
-    qv[5] = qv[3] / qv[1];
+    qv[3] = (qbr * qbr + qbi * qbi) * iy2;
+    gq = 4.0 * iy2 * sasy;
+    if (A.q) {
+      const double r1 = fast_rcp(qv[1]);
+      qv[4] = gq * r1;
+      qv[5] = qv[3] * r1;
+    }
   }
   if (A.q && valid) {
     double* qo = A.q + ((size_t)task * A.nx + i) * 6;
@@ -351,7 +357,9 @@ __global__ void __launch_bounds__(128, GM_COEFF_MINB) k_coeff(CoeffArgs A) {
     for (int k = 0; k < A.nmode; ++k) {
       double w = 0.0;
       if (valid) w = A.wscal ? A.wscal[((size_t)task * A.nmode + k) * A.nx + i] : wp;
-      double v[GM_NSCAL];
+      double v[16];
+#pragma unroll
+      for (int s = GM_NSCAL; s < 16; ++s) v[s] = 0.0;
       const bool on = act && (A.dense || w != 0.0);
       const double x2w = x2 * w, x4w = x4 * w;
       v[GM_S_W] = valid ? w : 0.0;
@@ -362,15 +370,13 @@ __global__ void __launch_bounds__(128, GM_COEFF_MINB) k_coeff(CoeffArgs A) {
       v[GM_S_QSCA] = on ? qv[1] * x2w : 0.0;
       v[GM_S_QABS] = on ? qv[2] * x2w : 0.0;
       v[GM_S_QB] = on ? qv[3] * x2w : 0.0;
-      v[GM_S_G] = on ? qv[4] * qv[1] * x2w : 0.0;
+      v[GM_S_G] = on ? gq * x2w : 0.0;
       v[GM_S_CSCA] = on ? qv[1] * qv[1] * x4w : 0.0;
       v[GM_S_CEXT] = on ? qv[0] * qv[1] * x4w : 0.0;
       double* o = A.scal_part + (((size_t)task * A.nmode + k) * A.ngroup + g) * GM_NSCAL;
-#pragma unroll
-      for (int s = 0; s < GM_NSCAL; ++s) {
-        double r = warp_sum(v[s]);
-        if (lane == 0) o[s] = r;
-      }
+      const double r = warp_reduce16(v, lane);
+      const int s = warp_reduce16_index(lane);
+      if (!(lane & 1) && s < GM_NSCAL) o[s] = r;
     }
   }
 }
