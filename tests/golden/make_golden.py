@@ -85,10 +85,37 @@ MINI = {
 }
 
 
-def dump_dataset(store):
+def _ref_data(name):
+    with open(os.path.join(rh.REF, "src", "geosmie", "data", name)) as fp:
+        return fp.read()
+
+
+def real_species():
+    """Shipped species configs (src/config/geosparticles/{oc,brc,ni}.json) with their REAL refractive-index files (OPAC/GADS
+    waso00 through the 'gads' reader, ri-brc.wsv, ri-nitrate.wsv: 61 wavelengths each), thinned in RH and grid density so that
+    the reference finishes in minutes.  ni keeps its three bins with per-bin rhop0 and size parameters up to ~7500."""
+    out = {}
+    for sp, keep_rh, npd in (("oc", [0, 30], 30), ("brc", [0, 35], 30), ("ni", [0, 26], 12)):
+        with open(os.path.join(rh.REF, "src", "config", "geosparticles", sp + ".json")) as fp:
+            cfg = json.load(fp)
+        cfg["rh"] = [cfg["rh"][i] for i in keep_rh]
+        cfg["rhDep"]["params"]["gf"] = [cfg["rhDep"]["params"]["gf"][i] for i in keep_rh]
+        cfg["psd"]["params"]["numperdec"] = [npd] * len(cfg["psd"]["params"]["numperdec"])
+        files = {path: _ref_data(os.path.basename(path)) for path in cfg["ri"]["path"]}
+        out[sp + "_real"] = (cfg, files)
+    return out
+
+
+THIN = [0, 13, 29, 44, 60]     # wavelength indices kept for the angle-resolved variables of the real-species fixtures
+
+
+def dump_dataset(store, thin=None):
     out = {}
     for k, v in store.variables.items():
-        out["var__" + k] = np.array(v.data)
+        a = np.array(v.data)
+        if thin is not None and a.ndim == 4 and "ang" in v.dimensions:
+            a = a[:, thin]
+        out["var__" + k] = a
         out["dims__" + k] = np.array("|".join(v.dimensions))
     for k, d in store.dimensions.items():
         out["dim__" + k] = np.array(len(d))
@@ -97,11 +124,14 @@ def dump_dataset(store):
 
 def gen_fun():
     """Full dointegration.fun (+ hydrophobic.doConversion) tables for the mini configs, new and legacy layout."""
-    for name, (cfg, files) in MINI.items():
+    allcfg = dict(MINI)
+    allcfg.update(real_species())
+    for name, (cfg, files) in allcfg.items():
         if ONLY and name not in ONLY:
             continue
+        thin = THIN if name.endswith("_real") else None
         extra = {name + ".json": json.dumps(cfg)}
-        extra.update(files)
+        extra.update({k: v for k, v in files.items() if not k.startswith("data/")})   # data/ is the reference's own directory
         for classic in (False, True):
             if classic and name not in ("bc_mini", "su_mini"):
                 continue
@@ -109,13 +139,15 @@ def gen_fun():
                 DI.fun(name + ".json", "json", d, classic)
                 fn = "optics_%s.nomom%s.nc4" % (name, ".legacy" if classic else "")
                 store = rh.registry()[os.path.join(d, fn)]
-                out = dump_dataset(store)
+                out = dump_dataset(store, thin)
                 if cfg.get("hydrophobic"):
                     # runoptics.py:113-121 renames the file first; the stub registry is keyed by path
                     rh.registry()[os.path.join(d, fn + ".nohp")] = store
                     R.hydrophobic.doConversion(fn + ".nohp", fn, d, classic)
-                    hp = dump_dataset(rh.registry()[os.path.join(d, fn)])
+                    hp = dump_dataset(rh.registry()[os.path.join(d, fn)], thin)
                     out.update({"hp__" + k: v for k, v in hp.items()})
+            if thin is not None:
+                out["thin_idx"] = np.array(thin)
             out["config_json"] = np.array(json.dumps(cfg))
             out["files_json"] = np.array(json.dumps(files))
             np.savez_compressed(os.path.join(HERE, "fun_%s%s.npz" % (name, "_legacy" if classic else "")), **out)
