@@ -11,6 +11,13 @@
 #include "gm_psd.cuh"
 #include "gm_gram.cuh"
 
+#ifndef GM_HIO_MIN_BATCHES
+#define GM_HIO_MIN_BATCHES 4     // host-buffer calls: batches whose H2D / D2H copies are pipelined against the kernels
+#endif
+#ifndef GM_EVAL_CTAS_PER_SM
+#define GM_EVAL_CTAS_PER_SM 2    // k_gram_eval: CTAs (angle block x task range) per SM
+#endif
+
 // ------------------------------------------------------------------------------------------------ errors / lifetime
 static thread_local char g_err[512] = "";
 
@@ -529,7 +536,7 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
     if ((rc = t->c_ab.ensure((size_t)tb * t->c_nab * sizeof(double4))) || (rc = t->c_scratch.ensure((size_t)tb * t->c_nscr * 8 * sizeof(double))))
       return rc;
   }
-  if (hio && ntask >= 256) tb = std::min(tb, (ntask + 3) / 4);   // at least 4 batches so that copies overlap compute
+  if (hio && ntask >= 256) tb = std::min(tb, (ntask + GM_HIO_MIN_BATCHES - 1) / GM_HIO_MIN_BATCHES);   // several batches so that copies overlap compute
   const bool use_gram = !per_particle && !(flags & GM_F_NO_GRAM) && !G.glist.empty();
   const int ndirect = use_gram ? G.ndirect : G.ngroup;
   // chunks of the per-angle contraction: enough CTAs to fill the machine ~8x over, cost-balanced by the k4 steps of the
@@ -773,7 +780,7 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
       GramEvalArgs EA;
       memset(&EA, 0, sizeof(EA));
       EA.ntask = nt;
-      EA.tasks_per_cta = std::max(1, (nt + (2 * h->sm_count / 4) - 1) / (2 * h->sm_count / 4));
+      EA.tasks_per_cta = std::max(1, (nt + (GM_EVAL_CTAS_PER_SM * h->sm_count / 4) - 1) / (GM_EVAL_CTAS_PER_SM * h->sm_count / 4));
       EA.hsum = SA.hsum;
       EA.N = N;
       EA.ntile = std::min((G.gram_nmax + 7) / 8, G.gram_tgmax);

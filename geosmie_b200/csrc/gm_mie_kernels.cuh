@@ -164,7 +164,7 @@ struct CoeffArgs {
 // MODE 0: DMMA group layout (c+ = (a+b) f_n sqrt(w), c- = (a-b) f_n sqrt(w)); MODE 1: natural a_n, b_n;
 // MODE 2: like MODE 0 but a_n, b_n are READ from the natural layout (coated spheres, produced by k_coated_coeff).
 #ifndef GM_COEFF_MINB
-#define GM_COEFF_MINB 5   // 96 registers, 20 warps per SM: 6 % faster than 3 (118 registers) on optics_SU, 6 spills at 6
+#define GM_COEFF_MINB 4   // 16 warps per SM without spills; at 5 (96 registers) the 16-value reduction spills 12 B and the kernel ran 1.9 ms instead of 1.05 ms on some boxes
 #endif
 template <int MODE>
 __global__ void __launch_bounds__(128, GM_COEFF_MINB) k_coeff(CoeffArgs A) {
