@@ -12,7 +12,7 @@
 #include "gm_gram.cuh"
 
 #ifndef GM_HIO_MIN_BATCHES
-#define GM_HIO_MIN_BATCHES 4     // host-buffer calls: batches whose H2D / D2H copies are pipelined against the kernels
+#define GM_HIO_MIN_BATCHES 3     // host-buffer calls: batches whose H2D / D2H copies are pipelined against the kernels (optics_SU e2e: 2 -> 3.92, 3 -> 3.72, 4 -> 3.87, 6 -> 4.1 ms)
 #endif
 #ifndef GM_EVAL_CTAS_PER_SM
 #define GM_EVAL_CTAS_PER_SM 2    // k_gram_eval: CTAs (angle block x task range) per SM

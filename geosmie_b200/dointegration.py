@@ -432,6 +432,11 @@ class BinPlan(object):
 
     def __init__(self, params, radind, lambarr, rh_used, part_m, water_m, cells=None, device_psd=False):
         self.radind = radind
+        if params['psd']['type'] == 'du':
+            # the reference's 'du' grid, (linspace(log10 x))**10 (dointegration.py:456-460), is not monotonic, so getDR and with
+            # it the number weights change sign along the grid (:640-648): build them with numpy like the reference and let
+            # evaluate() treat the two signs separately (the device folds sqrt(w) into the coefficients)
+            device_psd = False
         self.xx, self.dr = initializeXarr(params, radind, lambarr[0], lambarr[-1])
         self.nmax = nmax_of(self.xx)
         pparam = params['psd']['params']
@@ -518,7 +523,15 @@ class BinPlan(object):
             scal, phase = table.run_psd(mz, mz, self.psd_kind, par, fr, elide=elide)
         else:
             mz, wp, ws, tpc = self.tasks()
-            scal, phase = table.run(mz, mz, wp, ws, elide=elide)
+            neg = wp < 0
+            if neg.any():
+                # signed number weights: sums are linear in w, so phase = phase(w+) - phase(w-); the scalar sums take the signed
+                # per-mode weights as they are
+                scal, phase = table.run(mz, mz, np.where(neg, 0.0, wp), ws, elide=elide)
+                _, phase_n = table.run(mz, mz, np.where(neg, -wp, 0.0), None, elide=True)
+                phase = phase - phase_n
+            else:
+                scal, phase = table.run(mz, mz, wp, ws, elide=elide)
         return scal, phase, tpc
 
     def reduce(self, scal, phase, tasks_per_cell):

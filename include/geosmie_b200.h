@@ -100,7 +100,9 @@ int gm_table_set_bessel(gm_table_t t, const int64_t* off, const double* jv_half,
  * Replaces rawMie + calculateScatVals + the reductions of integratePSD (dointegration.py:1211-1254, :1044-1050,
  * :1104-1107, :1164-1166, :1188-1190); the caller combines the raw sums exactly like integratePSD does.
  *   mz/mrel [ntask][2]          as in gm_mie_eval (mu = 1: both sqrt(eps))
- *   w_phase [ntask][nx]         number weights for the phase-matrix sums
+ *   w_phase [ntask][nx]         number weights for the phase-matrix sums; must be >= 0 (sqrt(w) is folded into the coefficients).
+ *                               Signed weights (the reference's non-monotonic 'du' grid): call once with max(w, 0) and once
+ *                               with max(-w, 0) and subtract the phase sums -- the sums are linear in w
  *   w_scal  [ntask][nmode][nx]  number weights for the scalar sums (NULL: nmode must be 1 and w_phase is used)
  *   out_scal [ntask][nmode][GM_NSCAL]
  *   out_phase [ntask][4][nang]  sum_x w P(x,theta) for P11(=P22), P12, P33(=P44), P34

@@ -95,18 +95,25 @@ def real_species():
     waso00 through the 'gads' reader, ri-brc.wsv, ri-nitrate.wsv: 61 wavelengths each), thinned in RH and grid density so that
     the reference finishes in minutes.  ni keeps its three bins with per-bin rhop0 and size parameters up to ~7500."""
     out = {}
-    for sp, keep_rh, npd in (("oc", [0, 30], 30), ("brc", [0, 35], 30), ("ni", [0, 26], 12)):
+    for sp, keep_rh, npd in (("oc", [0, 30], 30), ("brc", [0, 35], 30), ("ni", [0, 26], 12),
+                             ("du-mie", [0, 20, 35], None),              # 'du' r^-4 sub-bin PSD on its fixed 1000-point grid, trivial rhDep
+                             ("v2.0.1/ss.v2.0.1", [0, 24, 35], 16),      # Gong sea salt, 5 bins, maxrh, OPAC sscm00 (gads)
+                             ("v2.0.1/bc.v5_7", [0, 33], 20),            # OPAC soot00 (gads), hydrophobic
+                             ("experimental/su_ht_reff04_sig16_single", [0, 35], 40)):
         with open(os.path.join(rh.REF, "src", "config", "geosparticles", sp + ".json")) as fp:
             cfg = json.load(fp)
         cfg["rh"] = [cfg["rh"][i] for i in keep_rh]
-        cfg["rhDep"]["params"]["gf"] = [cfg["rhDep"]["params"]["gf"][i] for i in keep_rh]
-        cfg["psd"]["params"]["numperdec"] = [npd] * len(cfg["psd"]["params"]["numperdec"])
+        if "gf" in cfg["rhDep"]["params"] and len(cfg["rhDep"]["params"]["gf"]) > 1:
+            cfg["rhDep"]["params"]["gf"] = [cfg["rhDep"]["params"]["gf"][i] for i in keep_rh]
+        if npd is not None:
+            cfg["psd"]["params"]["numperdec"] = [npd] * len(cfg["psd"]["params"]["numperdec"])
         files = {path: _ref_data(os.path.basename(path)) for path in cfg["ri"]["path"]}
-        out[sp + "_real"] = (cfg, files)
+        name = os.path.basename(sp).replace(".", "_").replace("-", "_")
+        out[name + "_real"] = (cfg, files)
     return out
 
 
-THIN = [0, 13, 29, 44, 60]     # wavelength indices kept for the angle-resolved variables of the real-species fixtures
+THIN = [0, 13, 29, 44, -1]     # wavelength indices kept for the angle-resolved variables of the real-species fixtures
 
 
 def dump_dataset(store, thin=None):
