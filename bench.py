@@ -18,7 +18,9 @@ One "step" = one pass of the hot path over that batch:
              are listed under roofline.kernels with their own bounds;
   cpu_baseline   the CPU oracle port (oracle/mie_oracle.c, OpenMP) on a bounded sample of the same cells.
 With --gpus N (torchrun) every rank evaluates its own 2196-cell shard of an N-times larger grid (weak scaling) and the
-reduced sums are gathered to rank 0 with NCCL inside the timed region.
+finished rows are gathered to rank 0 over NVLink inside the timed region: by default every rank's copy engine writes them
+into rank 0's CUDA-IPC-mapped buffer (geosmie_b200.dist.PeerGather); GEOSMIE_GATHER=store|nccl select the fused P2P-store
+variant or the NCCL gather.
 """
 import argparse
 import json
@@ -220,36 +222,75 @@ def main():
     scal_h = torch.empty((ncell, 1, _lib.GM_NSCAL), dtype=torch.float64).pin_memory()
     phase_h = torch.empty((ncell, 4, NANG), dtype=torch.float64).pin_memory()
     coef_h = torch.empty((ncell, 6, 129), dtype=torch.float64).pin_memory()
-    # multi-GPU: the finished rows of a step (sums, phase sums, GSF moments: 18 KB per cell) are gathered to rank 0 with NCCL.
-    # The gather of step k runs on NCCL's stream while step k+1 computes (two packed buffers); every gather is complete
-    # before the timed region ends.
+    # multi-GPU: the finished rows of a step (sums, phase sums, GSF moments: 18 KB per cell) go to rank 0 over NVLink.
+    # GEOSMIE_GATHER = peer (default): every rank's copy engine writes its rows into rank 0's buffer, mapped through CUDA
+    #                  IPC (gm_peer_put: no SM time on either GPU); the transfer of step k overlaps the kernels of step k+1;
+    #                = store: k_finalize and k_gsf store their results through the mapped pointers themselves (P2P stores);
+    #                = nccl: NCCL gather on NCCL's stream (two packed buffers).
+    # Every transfer is complete before the timed region ends (drain).
     pending = [None, None]
+    gather_mode = "none"
+    pg = None
+    nscal, nph, nco = ncell * _lib.GM_NSCAL, ncell * 4 * NANG, ncell * 6 * 129
     if world > 1:
-        width = _lib.GM_NSCAL + 4 * NANG + 6 * 129
-        packed = [torch.empty((ncell, width), dtype=torch.float64, device=dev) for _ in range(2)]
-        gather_buf = [[torch.empty_like(packed[0]) for _ in range(world)] if rank == 0 else None for _ in range(2)]
+        from geosmie_b200 import dist
+        comm = dist.Comm(rank, world, device=local)
+        gather_mode = os.environ.get("GEOSMIE_GATHER", "peer")
+        if gather_mode in ("peer", "store"):
+            pg = comm.peer_gather((nscal + nph + nco) * 8, nslot=2, handle=h)
+            if pg is None:
+                gather_mode = "nccl"
+        if gather_mode == "nccl":
+            width = _lib.GM_NSCAL + 4 * NANG + 6 * 129
+            packed = [torch.empty((ncell, width), dtype=torch.float64, device=dev) for _ in range(2)]
+            gather_buf = [[torch.empty_like(packed[0]) for _ in range(world)] if rank == 0 else None for _ in range(2)]
     step_no = [0]
 
-    def gather_rows():
+    def gather_rows(src=None):
+        """src = (scal, phase, coef) device pointers of this step's results (default: the bench's device tensors)."""
         i = step_no[0] & 1
         step_no[0] += 1
+        if gather_mode in ("peer", "store"):
+            if gather_mode == "store" and src is None:
+                return                          # the kernels of this step already stored into slot i (see step_device)
+            ps, pp_, pc = src or (scal_d.data_ptr(), phase_d.data_ptr(), coef_d.data_ptr())
+            pg.put(i, ps, nscal * 8, 0)
+            pg.put(i, pp_, nph * 8, nscal * 8)
+            pg.put(i, pc, nco * 8, (nscal + nph) * 8)
+            return
         if pending[i] is not None:
             pending[i].wait()                   # the buffer pair of two steps ago is free again
-        torch.cat([scal_d.reshape(ncell, -1), phase_d.reshape(ncell, -1), coef_d.reshape(ncell, -1)], dim=1, out=packed[i])
+        if src is None:
+            parts = [scal_d.reshape(ncell, -1), phase_d.reshape(ncell, -1), coef_d.reshape(ncell, -1)]
+        else:
+            parts = [_dev_view(p, n).reshape(ncell, -1) for p, n in zip(src, (nscal, nph, nco))]
+        torch.cat(parts, dim=1, out=packed[i])
         pending[i] = td.gather(packed[i], gather_buf[i], dst=0, async_op=True)
         if os.environ.get("GEOSMIE_BENCH_GATHER_SYNC"):      # diagnostic: no overlap with the next step
             pending[i].wait()
             pending[i] = None
 
+    def _dev_view(p, n):
+        class _A(object):
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (int(p), False), "version": 3}
+        return torch.as_tensor(_A(), device=dev)
+
     def drain():
+        if pg is not None:
+            pg.join()                           # the compute stream (and the closing event) waits for the exchange stream
         for i in range(2):
             if pending[i] is not None:
                 pending[i].wait()
                 pending[i] = None
 
     def step_device():
+        coef_ptr = coef_d.data_ptr()
+        if gather_mode == "store":
+            i = step_no[0] & 1
+            table.set_mirror(pg.seg_ptr(i, 0), pg.seg_ptr(i, nscal * 8))
+            coef_ptr = pg.seg_ptr(i, (nscal + nph) * 8)     # k_gsf writes the moments straight into rank 0's buffer
         table.run_dev(ncell, mz_d.data_ptr(), mz_d.data_ptr(), 1, w_d.data_ptr(), 0, scal_d.data_ptr(), phase_d.data_ptr(), elide=False)
-        h.gsf_expand_phase4_dev(ang, ncell, phase_d.data_ptr(), coef_d.data_ptr(), cn_d.data_ptr())
+        h.gsf_expand_phase4_dev(ang, ncell, phase_d.data_ptr(), coef_ptr, cn_d.data_ptr())
         if world > 1:
             gather_rows()
 
@@ -269,7 +310,7 @@ def main():
         # kernels, and D2H of the reduced sums and GSF moments pipelined batch by batch inside the library
         table.run_psd(mz_psd, mz_psd, psd_kind, psd_par, psd_frac, elide=False, out=(scal_hn, phase_hn))
         if world > 1:
-            gather_rows()
+            gather_rows(e2e_src[0])
 
     def barrier():
         if world > 1:
@@ -304,7 +345,12 @@ def main():
     launches = (h.launch_count() - launches0) // args.steps
     kms = table.last_kernel_ms()            # CUDA events around the launches of the LAST timed step
     stats = table.last_stats()
+    table.set_mirror(None, None)
     table.set_gsf(ang, 129, False, coef_hn, None)
+    e2e_src = [None]
+    if world > 1:
+        table.run_psd(mz_psd, mz_psd, psd_kind, psd_par, psd_frac, elide=False, out=(scal_hn, phase_hn))
+        e2e_src[0] = table.device_outputs() + (table.gsf_device()[0],)   # the library's device copies of the results
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
@@ -347,7 +393,10 @@ def main():
         "config": {"workload": "optics_SU dense table build: 1 bin x 4459 sizes x 61 lambda x 36 RH = 2196 cells, 371 angles, "
                                "then 129 GSF moments x 6 per cell", "cells_per_gpu": ncell, "nx": nx, "nang": NANG,
                    "l2_policy": "inputs larger than L2 per step: 78 MB weights + 2.9 GB coefficient stream + 0.66 GB partial Gram blocks re-written every step",
-                   "parallelism": "cells sharded, %d rank(s), NCCL gather to rank 0 (overlapped with the next step, complete inside the timed region)" % world},
+                   "parallelism": "cells sharded, %d rank(s), gather to rank 0: %s (overlapped with the next step, complete inside the timed region)"
+                                  % (world, {"peer": "copy-engine puts into rank 0's IPC-mapped buffer over NVLink (gm_peer_put)",
+                                             "store": "P2P stores of k_finalize / k_gsf into rank 0's IPC-mapped buffer",
+                                             "nccl": "NCCL gather", "none": "none (1 rank)"}[gather_mode])},
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(mz_psd.nbytes * 2 + psd_par.nbytes + psd_frac.nbytes),
                 "api": "gm_table_run_psd with the fused GSF stage (host buffers: per-cell m and PSD parameters in, reduced sums and GSF moments out)",
@@ -387,6 +436,7 @@ def main():
         print(json.dumps(line))
     table.close()
     if world > 1:
+        comm.close()
         td.destroy_process_group()
 
 

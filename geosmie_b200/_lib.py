@@ -55,7 +55,16 @@ SIGNATURES = {
     "gm_gsf_expand_dev": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int]),
     "gm_gsf_expand_phase4_dev": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int]),
     "gm_band_average": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int, vp]),
+    "gm_peer_alloc": (C.c_int, [vp, C.c_size_t, C.POINTER(vp), vp]),
+    "gm_peer_free": (C.c_int, [vp, vp]),
+    "gm_peer_open": (C.c_int, [vp, vp, C.POINTER(vp)]),
+    "gm_peer_close": (C.c_int, [vp, vp]),
+    "gm_peer_put": (C.c_int, [vp, vp, vp, C.c_size_t]),
+    "gm_peer_join": (C.c_int, [vp]),
+    "gm_peer_sync": (C.c_int, [vp]),
+    "gm_table_set_mirror": (C.c_int, [vp, vp, vp]),
 }
+IPC_HANDLE_BYTES = 64
 
 
 class GeosmieError(RuntimeError):
@@ -129,6 +138,36 @@ class Handle:
 
     def launch_count(self):
         return int(self.lib.gm_launch_count(self.h))
+
+    # ---- multi-GPU exchange over peer memory (gm_peer.cu) ------------------------------------------------------------
+    def peer_alloc(self, nbytes):
+        """-> (device pointer, 64-byte CUDA IPC handle) of a new exchange buffer on this GPU."""
+        p = vp()
+        hd = C.create_string_buffer(IPC_HANDLE_BYTES)
+        check(self.lib.gm_peer_alloc(self.h, int(nbytes), C.byref(p), C.cast(hd, vp)))
+        return p.value, hd.raw
+
+    def peer_free(self, dptr):
+        check(self.lib.gm_peer_free(self.h, vp(dptr)))
+
+    def peer_open(self, ipc_handle):
+        p = vp()
+        hd = C.create_string_buffer(bytes(ipc_handle), IPC_HANDLE_BYTES)
+        check(self.lib.gm_peer_open(self.h, C.cast(hd, vp), C.byref(p)))
+        return p.value
+
+    def peer_close(self, dptr):
+        check(self.lib.gm_peer_close(self.h, vp(dptr)))
+
+    def peer_put(self, dst_ptr, src_ptr, nbytes):
+        """Copy-engine transfer on the exchange stream, ordered after the compute stream's current work."""
+        check(self.lib.gm_peer_put(self.h, vp(dst_ptr), vp(src_ptr), int(nbytes)))
+
+    def peer_join(self):
+        check(self.lib.gm_peer_join(self.h))
+
+    def peer_sync(self):
+        check(self.lib.gm_peer_sync(self.h))
 
     # ---- per-particle Mie ------------------------------------------------------------------------------------------
     def mie_eval(self, x, mz, mrel, nmax, u=None, xcore=None, ajv=None, ayv=None, want_s12=True, want_ab=False):
@@ -266,6 +305,10 @@ class Table:
         self._gsf_keep = (ang, coef_out, cnorm_out)
         check(self.lib.gm_table_set_gsf(self.t, ptr(ang), int(ng), int(bool(quantize10)), ptr(coef_out), ptr(cnorm_out)))
 
+    def set_mirror(self, scal_ptr, phase_ptr):
+        """k_finalize also stores its results through these (peer) device pointers; (None, None) switches it off."""
+        check(self.lib.gm_table_set_mirror(self.t, vp(scal_ptr) if scal_ptr else None, vp(phase_ptr) if phase_ptr else None))
+
     def set_dr(self, dr):
         check(self.lib.gm_table_set_dr(self.t, ptr(f64(dr))))
 
@@ -295,6 +338,12 @@ class Table:
         """Host-buffer call writing into caller-provided (ideally pinned) numpy arrays; single-mode weights."""
         check(self.lib.gm_table_run(self.t, ntask, ptr(mz), ptr(mrel), 1, ptr(w_phase), None, self._flags(elide),
                                     ptr(scal_out), ptr(phase_out)))
+
+    def gsf_device(self):
+        """Device pointers (coef [ntask][6][ng], cnorm [ntask]) of the fused GSF stage's results."""
+        a, b = vp(), vp()
+        check(self.lib.gm_table_gsf_device(self.t, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def device_outputs(self):
         a, b = vp(), vp()

@@ -72,6 +72,9 @@ extern "C" int gm_destroy(gm_handle_t h) {
     b->release();
   h->gsf_nodes.release();
   h->gsf_table.release();
+  if (h->peer_stream) cudaStreamDestroy(h->peer_stream);
+  if (h->peer_ev_compute) cudaEventDestroy(h->peer_ev_compute);
+  if (h->peer_ev_done) cudaEventDestroy(h->peer_ev_done);
   delete h;
   return GM_OK;
 }
@@ -335,6 +338,9 @@ struct gm_table_s {
   double* gsf_coef_host = nullptr;
   double* gsf_cnorm_host = nullptr;
   DevBuf gsf_coef, gsf_cnorm;
+  // gm_table_set_mirror: second (peer-memory) destination of k_finalize's results
+  double* mirror_scal = nullptr;
+  double* mirror_phase = nullptr;
   long long c_nab = 0, c_nscr = 0;
   bool have_dr = false;
   bool psd_separate = false;
@@ -812,7 +818,9 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
     if (!per_particle) {
       if ((rc = ev_mark(t, 2))) return rc;
       k_finalize<<<nt, GM_NANG_PAD, 0, st>>>(nchunk_total, G.ngroup, nmode, t->nang, t->h->scratch_part.as<double>(), t->h->scratch_scal_part.as<double>(),
-                                             d_out_phase + (size_t)t0 * 4 * t->nang, d_out_scal + (size_t)t0 * nmode * GM_NSCAL);
+                                             d_out_phase + (size_t)t0 * 4 * t->nang, d_out_scal + (size_t)t0 * nmode * GM_NSCAL,
+                                             t->mirror_phase ? t->mirror_phase + (size_t)t0 * 4 * t->nang : nullptr,
+                                             t->mirror_scal ? t->mirror_scal + (size_t)t0 * nmode * GM_NSCAL : nullptr);
       GM_LAUNCH_CHECK(h);
       if ((rc = ev_mark(t, 2))) return rc;
       if (t->gsf_ng > 0) {
@@ -945,6 +953,14 @@ extern "C" int gm_table_set_gsf(gm_table_t t, const double* ang_deg, int ng, int
   t->gsf_quant = quantize10;
   t->gsf_coef_host = coef_host;
   t->gsf_cnorm_host = cnorm_host;
+  return GM_OK;
+}
+
+extern "C" int gm_table_set_mirror(gm_table_t t, double* scal_mirror, double* phase_mirror) {
+  GM_REQUIRE(t != nullptr, "table is NULL");
+  GM_REQUIRE((scal_mirror == nullptr) == (phase_mirror == nullptr), "give both mirror pointers or neither");
+  t->mirror_scal = scal_mirror;
+  t->mirror_phase = phase_mirror;
   return GM_OK;
 }
 

@@ -71,6 +71,10 @@ struct gm_handle_s {
   // GSF constants (Gauss nodes, interpolation brackets, generalized spherical functions) cached per angle grid
   DevBuf gsf_nodes, gsf_table;
   std::vector<double> gsf_key;
+  // multi-GPU exchange (gm_peer.cu): copy-engine transfers run on their own stream, ordered against `stream` by events
+  cudaStream_t peer_stream = nullptr;
+  cudaEvent_t peer_ev_compute = nullptr, peer_ev_done = nullptr;
+  bool peer_pending = false;
 };
 
 // GSF expansion of gm_table_run's phase layout on device pointers (gm_gsf.cu); asynchronous on the handle's stream

@@ -618,9 +618,12 @@ __global__ void __launch_bounds__(GM_CONTRACT_THREADS, 1) k_contract(ContractArg
 // grid = ntask, block = GM_NANG_PAD.  Sums the chunk partials in chunk order and the group partials in group order.
 //   p11 = (A + B)/4, p12 = -C_r/2, p33 = (A - B)/4, p34 = -C_i/2  with A = sum w|S+|^2, B = sum w|S-|^2, C = sum w S+ S-*
 //   (S1 = (S+ + S-)/2, S2 = (S+ - S-)/2 in calculateScatVals, dointegration.py:1044-1050)
+//   mirror_phase / mirror_scal (nullable): a second destination with the same layout -- the segment of this rank in rank 0's
+//   gather buffer, mapped through CUDA IPC, so that the multi-GPU gather is part of this kernel (P2P stores over NVLink)
 __global__ void __launch_bounds__(GM_NANG_PAD) k_finalize(int nchunk, int ngroup, int nmode, int nang, const double* __restrict__ part,
                                                          const double* __restrict__ scal_part, double* __restrict__ out_phase,
-                                                         double* __restrict__ out_scal) {
+                                                         double* __restrict__ out_scal, double* __restrict__ mirror_phase,
+                                                         double* __restrict__ mirror_scal) {
   const int task = blockIdx.x, a = threadIdx.x;
   if (a < nang) {
     double s[4] = {0, 0, 0, 0};
@@ -630,10 +633,18 @@ __global__ void __launch_bounds__(GM_NANG_PAD) k_finalize(int nchunk, int ngroup
       for (int q = 0; q < 4; ++q) s[q] += p[(size_t)q * GM_NANG_PAD];
     }
     double* o = out_phase + (size_t)task * 4 * nang + a;
-    o[0] = 0.25 * (s[0] + s[1]);
-    o[(size_t)nang] = -0.5 * s[2];
-    o[(size_t)2 * nang] = 0.25 * (s[0] - s[1]);
-    o[(size_t)3 * nang] = -0.5 * s[3];
+    const double p11 = 0.25 * (s[0] + s[1]), p12 = -0.5 * s[2], p33 = 0.25 * (s[0] - s[1]), p34 = -0.5 * s[3];
+    o[0] = p11;
+    o[(size_t)nang] = p12;
+    o[(size_t)2 * nang] = p33;
+    o[(size_t)3 * nang] = p34;
+    if (mirror_phase) {
+      double* m = mirror_phase + (size_t)task * 4 * nang + a;
+      m[0] = p11;
+      m[(size_t)nang] = p12;
+      m[(size_t)2 * nang] = p33;
+      m[(size_t)3 * nang] = p34;
+    }
   }
   if (a < nmode * GM_NSCAL) {
     const int k = a / GM_NSCAL, q = a % GM_NSCAL;
@@ -641,6 +652,7 @@ __global__ void __launch_bounds__(GM_NANG_PAD) k_finalize(int nchunk, int ngroup
     double s = 0.0;
     for (int g = 0; g < ngroup; ++g) s += p[(size_t)g * GM_NSCAL];
     out_scal[((size_t)task * nmode + k) * GM_NSCAL + q] = s;
+    if (mirror_scal) mirror_scal[((size_t)task * nmode + k) * GM_NSCAL + q] = s;
   }
 }
 

@@ -195,6 +195,33 @@ int gm_gsf_expand_phase4_dev(gm_handle_t h, int ncell, int nang, const double* a
 int gm_band_average(gm_handle_t h, int ncol, int nlam, const double* lam, const double* v, int nband, const double* lo,
                     const double* hi, int use_wavenum, double* out);
 
+/* ---- multi-GPU exchange over NVLink peer memory -------------------------------------------------------------
+ * The reference has no multi-process table build (its only parallelism is one process per species,
+ * proc.v2.1.0.csh:30-33; dointegration.py:804-810 notes that the (wavelength, RH) cells are independent).  Here cells are
+ * sharded over one process per GPU and the finished rows of every rank land in ONE device buffer on rank 0, which every
+ * rank maps through CUDA IPC:
+ *   rank 0:  gm_peer_alloc  -> device pointer + a 64-byte IPC handle (sent to the other ranks by the caller, e.g. through
+ *            torch.distributed broadcast);      other ranks: gm_peer_open(handle) -> the same memory in their address space.
+ *   gm_peer_put   copy-engine transfer (no SMs on either side) src -> dst, asynchronous on the handle's exchange stream and
+ *                 ordered after everything enqueued so far on the handle's compute stream; src/dst: device, peer or pinned
+ *                 host memory (cudaMemcpyDefault), so it also serves rank 0's read-out.
+ *   gm_peer_join  the compute stream waits for all puts issued so far (e.g. before an event that closes a timed region);
+ *   gm_peer_sync  the host waits for them.  After gm_peer_sync on every rank + a barrier the data is complete on rank 0.
+ *   gm_table_set_mirror  fused variant: k_finalize of every following gm_table_run* call ALSO stores its results through
+ *                 the given (peer) pointers, [ntask][nmode][GM_NSCAL] and [ntask][4][nang], so the transfer is part of the
+ *                 producing kernel (P2P stores over NVLink) and needs no extra pass; gm_gsf_expand_phase4_dev accepts a
+ *                 peer pointer for `coef` likewise.  NULL, NULL switches it off.
+ */
+#define GM_IPC_HANDLE_BYTES 64
+int gm_peer_alloc(gm_handle_t h, size_t bytes, void** dptr, unsigned char ipc_handle[GM_IPC_HANDLE_BYTES]);
+int gm_peer_free(gm_handle_t h, void* dptr);
+int gm_peer_open(gm_handle_t h, const unsigned char ipc_handle[GM_IPC_HANDLE_BYTES], void** dptr);
+int gm_peer_close(gm_handle_t h, void* dptr);
+int gm_peer_put(gm_handle_t h, void* dst, const void* src, size_t bytes);
+int gm_peer_join(gm_handle_t h);
+int gm_peer_sync(gm_handle_t h);
+int gm_table_set_mirror(gm_table_t t, double* scal_mirror, double* phase_mirror);
+
 #ifdef __cplusplus
 }
 #endif
