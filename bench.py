@@ -215,9 +215,12 @@ def main():
     mz_h = torch.from_numpy(np.ascontiguousarray(mz_np).view(np.float64).reshape(ncell, 2).copy()).pin_memory()
     w_h = torch.from_numpy(np.ascontiguousarray(wp_np)).pin_memory()
     mz_d, w_d = mz_h.to(dev), w_h.to(dev)
-    scal_d = torch.empty((ncell, 1, _lib.GM_NSCAL), dtype=torch.float64, device=dev)
-    phase_d = torch.empty((ncell, 4, NANG), dtype=torch.float64, device=dev)
-    coef_d = torch.empty((ncell, 6, 129), dtype=torch.float64, device=dev)
+    # two sets of device outputs: with more than one rank the copy engine may still be reading the rows of step k-1 while
+    # step k computes (the fences gm_peer_wait / gm_peer_mark order the reuse two steps later)
+    outs_d = [(torch.empty((ncell, 1, _lib.GM_NSCAL), dtype=torch.float64, device=dev),
+               torch.empty((ncell, 4, NANG), dtype=torch.float64, device=dev),
+               torch.empty((ncell, 6, 129), dtype=torch.float64, device=dev)) for _ in range(2 if world > 1 else 1)]
+    scal_d, phase_d, coef_d = outs_d[0]
     cn_d = torch.empty((ncell,), dtype=torch.float64, device=dev)
     scal_h = torch.empty((ncell, 1, _lib.GM_NSCAL), dtype=torch.float64).pin_memory()
     phase_h = torch.empty((ncell, 4, NANG), dtype=torch.float64).pin_memory()
@@ -247,21 +250,24 @@ def main():
     step_no = [0]
 
     def gather_rows(src=None):
-        """src = (scal, phase, coef) device pointers of this step's results (default: the bench's device tensors)."""
+        """src = (scal, phase, coef) device pointers of this step's results (default: the bench's device tensors of this
+        step's parity)."""
         i = step_no[0] & 1
         step_no[0] += 1
+        sd, pd, cd = outs_d[i % len(outs_d)]
         if gather_mode in ("peer", "store"):
             if gather_mode == "store" and src is None:
                 return                          # the kernels of this step already stored into slot i (see step_device)
-            ps, pp_, pc = src or (scal_d.data_ptr(), phase_d.data_ptr(), coef_d.data_ptr())
+            ps, pp_, pc = src or (sd.data_ptr(), pd.data_ptr(), cd.data_ptr())
             pg.put(i, ps, nscal * 8, 0)
             pg.put(i, pp_, nph * 8, nscal * 8)
             pg.put(i, pc, nco * 8, (nscal + nph) * 8)
+            h.peer_mark(i)
             return
         if pending[i] is not None:
             pending[i].wait()                   # the buffer pair of two steps ago is free again
         if src is None:
-            parts = [scal_d.reshape(ncell, -1), phase_d.reshape(ncell, -1), coef_d.reshape(ncell, -1)]
+            parts = [sd.reshape(ncell, -1), pd.reshape(ncell, -1), cd.reshape(ncell, -1)]
         else:
             parts = [_dev_view(p, n).reshape(ncell, -1) for p, n in zip(src, (nscal, nph, nco))]
         torch.cat(parts, dim=1, out=packed[i])
@@ -284,13 +290,16 @@ def main():
                 pending[i] = None
 
     def step_device():
-        coef_ptr = coef_d.data_ptr()
-        if gather_mode == "store":
-            i = step_no[0] & 1
+        i = step_no[0] & 1
+        sd, pd, cd = outs_d[i % len(outs_d)]
+        coef_ptr = cd.data_ptr()
+        if gather_mode == "peer":
+            h.peer_wait(i)                                   # the put of two steps ago has finished reading this output set
+        elif gather_mode == "store":
             table.set_mirror(pg.seg_ptr(i, 0), pg.seg_ptr(i, nscal * 8))
             coef_ptr = pg.seg_ptr(i, (nscal + nph) * 8)     # k_gsf writes the moments straight into rank 0's buffer
-        table.run_dev(ncell, mz_d.data_ptr(), mz_d.data_ptr(), 1, w_d.data_ptr(), 0, scal_d.data_ptr(), phase_d.data_ptr(), elide=False)
-        h.gsf_expand_phase4_dev(ang, ncell, phase_d.data_ptr(), coef_ptr, cn_d.data_ptr())
+        table.run_dev(ncell, mz_d.data_ptr(), mz_d.data_ptr(), 1, w_d.data_ptr(), 0, sd.data_ptr(), pd.data_ptr(), elide=False)
+        h.gsf_expand_phase4_dev(ang, ncell, pd.data_ptr(), coef_ptr, cn_d.data_ptr())
         if world > 1:
             gather_rows()
 
@@ -308,9 +317,13 @@ def main():
     def step_e2e():
         # the user-facing call with HOST buffers (gm_table_run_psd with the fused GSF stage): H2D of this step's inputs,
         # kernels, and D2H of the reduced sums and GSF moments pipelined batch by batch inside the library
+        if pg is not None:
+            h.peer_wait(2)                      # the library's device copies of the last step's rows have been sent
         table.run_psd(mz_psd, mz_psd, psd_kind, psd_par, psd_frac, elide=False, out=(scal_hn, phase_hn))
         if world > 1:
             gather_rows(e2e_src[0])
+            if pg is not None:
+                h.peer_mark(2)
 
     def barrier():
         if world > 1:

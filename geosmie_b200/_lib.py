@@ -54,6 +54,8 @@ SIGNATURES = {
     "gm_gsf_expand": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int]),
     "gm_gsf_expand_dev": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int]),
     "gm_gsf_expand_phase4_dev": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int]),
+    "gm_gsf_diagnose": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int, vp, vp]),
+    "gm_gsf_diagnose_dev": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp]),
     "gm_band_average": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int, vp]),
     "gm_peer_alloc": (C.c_int, [vp, C.c_size_t, C.POINTER(vp), vp]),
     "gm_peer_free": (C.c_int, [vp, vp]),
@@ -62,6 +64,8 @@ SIGNATURES = {
     "gm_peer_put": (C.c_int, [vp, vp, vp, C.c_size_t]),
     "gm_peer_join": (C.c_int, [vp]),
     "gm_peer_sync": (C.c_int, [vp]),
+    "gm_peer_mark": (C.c_int, [vp, C.c_int]),
+    "gm_peer_wait": (C.c_int, [vp, C.c_int]),
     "gm_table_set_mirror": (C.c_int, [vp, vp, vp]),
 }
 IPC_HANDLE_BYTES = 64
@@ -169,6 +173,14 @@ class Handle:
     def peer_sync(self):
         check(self.lib.gm_peer_sync(self.h))
 
+    def peer_mark(self, idx):
+        """Remember 'all puts issued so far' under mark idx (0..3)."""
+        check(self.lib.gm_peer_mark(self.h, int(idx)))
+
+    def peer_wait(self, idx):
+        """The compute stream waits for mark idx (no-op if it was never recorded)."""
+        check(self.lib.gm_peer_wait(self.h, int(idx)))
+
     # ---- per-particle Mie ------------------------------------------------------------------------------------------
     def mie_eval(self, x, mz, mrel, nmax, u=None, xcore=None, ajv=None, ayv=None, want_s12=True, want_ab=False):
         x = f64(np.atleast_1d(x))
@@ -207,6 +219,21 @@ class Handle:
         cnorm = np.empty(ncell)
         check(self.lib.gm_gsf_expand(self.h, ncell, ang.size, ptr(ang), ptr(F), ng, ptr(coef), ptr(cnorm), int(bool(quantize10))))
         return coef, cnorm
+
+    def gsf_diagnose(self, ang_deg, F, ng=129, quantize10=False):
+        """gsf_expand + the diagnostics of spher_expan.f: -> (coef, cnorm, fout [ncell][6][nang] = the .expan_matr columns,
+        fiterr [ncell])."""
+        ang = f64(ang_deg)
+        F = f64(F)
+        ncell = F.shape[0]
+        assert F.shape[1:] == (6, ang.size)
+        coef = np.empty((ncell, 6, ng))
+        cnorm = np.empty(ncell)
+        fout = np.empty((ncell, 6, ang.size))
+        fiterr = np.empty(ncell)
+        check(self.lib.gm_gsf_diagnose(self.h, ncell, ang.size, ptr(ang), ptr(F), ng, ptr(coef), ptr(cnorm), int(bool(quantize10)),
+                                       ptr(fout), ptr(fiterr)))
+        return coef, cnorm, fout, fiterr
 
     def gsf_expand_phase4_dev(self, ang_deg, ncell, p4_ptr, coef_ptr, cnorm_ptr, ng=129, quantize10=False):
         """Device-pointer GSF expansion of gm_table_run's out_phase (asynchronous except for the small table upload)."""

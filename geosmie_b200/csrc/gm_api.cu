@@ -72,9 +72,13 @@ extern "C" int gm_destroy(gm_handle_t h) {
     b->release();
   h->gsf_nodes.release();
   h->gsf_table.release();
+  h->gsf_alt.release();
+  h->gsf_raw.release();
   if (h->peer_stream) cudaStreamDestroy(h->peer_stream);
   if (h->peer_ev_compute) cudaEventDestroy(h->peer_ev_compute);
   if (h->peer_ev_done) cudaEventDestroy(h->peer_ev_done);
+  for (cudaEvent_t e : h->peer_marks)
+    if (e) cudaEventDestroy(e);
   delete h;
   return GM_OK;
 }

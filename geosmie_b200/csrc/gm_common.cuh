@@ -69,11 +69,13 @@ struct gm_handle_s {
   // handle, so that building one table per size bin does not pay a multi-GB cudaMalloc / cudaFree per bin
   DevBuf scratch_coef, scratch_gact, scratch_scal_part, scratch_part, scratch_g_hpart, scratch_g_hsum, scratch_wphase, scratch_wscal;
   // GSF constants (Gauss nodes, interpolation brackets, generalized spherical functions) cached per angle grid
-  DevBuf gsf_nodes, gsf_table;
+  DevBuf gsf_nodes, gsf_table, gsf_alt, gsf_raw;
   std::vector<double> gsf_key;
+  bool gsf_alt_valid = false;
   // multi-GPU exchange (gm_peer.cu): copy-engine transfers run on their own stream, ordered against `stream` by events
   cudaStream_t peer_stream = nullptr;
   cudaEvent_t peer_ev_compute = nullptr, peer_ev_done = nullptr;
+  cudaEvent_t peer_marks[4] = {nullptr, nullptr, nullptr, nullptr};   // gm_peer_mark / gm_peer_wait
   bool peer_pending = false;
 };
 

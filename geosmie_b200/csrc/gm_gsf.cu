@@ -117,7 +117,7 @@ struct GsfNode {
 // nrow = 6: F rows are F11,F22,F33,F44,F12,F34.  nrow = 4: rows are P11,P12,P33,P34 of gm_table_run (P22 = P11, P44 = P33).
 __global__ void __launch_bounds__(256) k_gsf(int nrow, int nang, int ng, const double* __restrict__ F, const GsfNode* __restrict__ nodes,
                                              const double* __restrict__ G, double* __restrict__ coef, double* __restrict__ cnorm,
-                                             int quantize10) {
+                                             int quantize10, double* __restrict__ raw) {
   extern __shared__ double sm[];
   double* f = sm;                 // [6][nang]
   double* ff = sm + 6 * nang;     // [6][ng]: FF11, FP, FM, FF44, FF12, FF34
@@ -174,9 +174,146 @@ __global__ void __launch_bounds__(256) k_gsf(int nrow, int nang, int ng, const d
       double v = o[k] * cn;
       if (quantize10) v = rint(v * 1e10) / 1e10;
       coef[((size_t)cell * 6 + k) * ng + l] = v;
+      if (raw) raw[((size_t)cell * 6 + k) * ng + l] = o[k];   // as SPHER_EXPAN leaves them: the input of MATR (one_calc :168-173)
     }
   }
   if (threadIdx.x == 0 && cnorm) cnorm[cell] = cn;
+}
+
+// ------------------------------------------------------------------------------------------------ diagnostics
+// The diagnostic half of spher_expan.f: MATR (:419-517) re-synthesises the matrix from the un-normalised coefficients at the
+// input angles (what main writes to <file>.expan_matr, :84-90) and at READMATRIX's alternative grid (:237-258, USE_ALT_ANG = 1);
+// fiterr = max |F11 - F11OUT| over both (ERREVAL, ERRTYP = MAXABS, range [0, 180] deg; one_calc :168-177).
+struct GsfAlt {
+  double u;          // cos(angl(i))       (host libm, like the oracle)
+  double ualt;       // cos(alt_angl(i))
+  double num, dx;    // LINTERPOL bracket of alt_angl(i) in the input grid, in DEGREES (READMATRIX interpolates before the D2R scaling)
+  int i0, i1;
+  int inrange;       // ang_min <= angl(i) <= ang_max
+  int pad;
+};
+
+// one MATR angle; no FMA contraction (the oracle is compiled without FMA)
+__device__ __forceinline__ void gsf_matr_angle(int ng, const double* __restrict__ c, double U, double (&F)[6]) {
+  const double* A1 = c, *A2 = c + ng, *A3 = c + 2 * ng, *A4 = c + 3 * ng, *B1 = c + 4 * ng, *B2 = c + 5 * ng;
+  const int LMAX = ng - 1;
+  const double D6 = __dmul_rn(sqrt(6.0), 0.25);
+  double F11 = 0, F2 = 0, F3 = 0, F44 = 0, F12 = 0, F34 = 0, P1 = 0, P2 = 0, P3 = 0, P4 = 0;
+  double PP1 = 1.0;
+  const double up = __dadd_rn(1.0, U), um = __dsub_rn(1.0, U);
+  double PP2 = __dmul_rn(__dmul_rn(0.25, up), up);
+  double PP3 = __dmul_rn(__dmul_rn(0.25, um), um);
+  double PP4 = __dmul_rn(D6, __dsub_rn(__dmul_rn(U, U), 1.0));
+  for (int L1 = 1; L1 <= ng; ++L1) {
+    const int L = L1 - 1;
+    const double DL = (double)L, DL1 = (double)L1, PL1 = (double)(2 * L + 1);
+    F11 = __dadd_rn(F11, __dmul_rn(A1[L], PP1));
+    F44 = __dadd_rn(F44, __dmul_rn(A4[L], PP1));
+    if (L != LMAX) {
+      const double P = __ddiv_rn(__dsub_rn(__dmul_rn(__dmul_rn(PL1, U), PP1), __dmul_rn(DL, P1)), DL1);
+      P1 = PP1;
+      PP1 = P;
+    }
+    if (L < 2) continue;
+    F2 = __dadd_rn(F2, __dmul_rn(__dadd_rn(A2[L], A3[L]), PP2));
+    F3 = __dadd_rn(F3, __dmul_rn(__dsub_rn(A2[L], A3[L]), PP3));
+    F12 = __dadd_rn(F12, __dmul_rn(B1[L], PP4));
+    F34 = __dadd_rn(F34, __dmul_rn(B2[L], PP4));
+    if (L == LMAX) continue;
+    const double PL2 = __dmul_rn(__dmul_rn(DL, DL1), U);
+    const double PL3 = __dmul_rn(DL1, __dsub_rn(__dmul_rn(DL, DL), 4.0));
+    const double PL4 = __ddiv_rn(1.0, __dmul_rn(DL, __dsub_rn(__dmul_rn(DL1, DL1), 4.0)));
+    double P = __dmul_rn(__dsub_rn(__dmul_rn(__dmul_rn(PL1, __dsub_rn(PL2, 4.0)), PP2), __dmul_rn(PL3, P2)), PL4);
+    P2 = PP2;
+    PP2 = P;
+    P = __dmul_rn(__dsub_rn(__dmul_rn(__dmul_rn(PL1, __dadd_rn(PL2, 4.0)), PP3), __dmul_rn(PL3, P3)), PL4);
+    P3 = PP3;
+    PP3 = P;
+    P = __ddiv_rn(__dsub_rn(__dmul_rn(__dmul_rn(PL1, U), PP4), __dmul_rn(__dsqrt_rn(__dsub_rn(__dmul_rn(DL, DL), 4.0)), P4)),
+                  __dsqrt_rn(__dsub_rn(__dmul_rn(DL1, DL1), 4.0)));
+    P4 = PP4;
+    PP4 = P;
+  }
+  F[0] = F11;
+  F[1] = __dmul_rn(__dadd_rn(F2, F3), 0.5);
+  F[2] = __dmul_rn(__dsub_rn(F2, F3), 0.5);
+  F[3] = F44;
+  F[4] = F12;
+  F[5] = F34;
+}
+
+// CTA per cell, thread per (grid, angle).  F11 of the cell is row 0 for both input layouts (nrow = 6 or 4).
+__global__ void __launch_bounds__(256) k_gsf_matr(int nrow, int nang, int ng, const double* __restrict__ F, const double* __restrict__ raw,
+                                                  const GsfAlt* __restrict__ alt, double* __restrict__ fout, double* __restrict__ fiterr) {
+  extern __shared__ double sm[];
+  double* c = sm;              // [6][ng]
+  double* f11 = sm + 6 * ng;   // [nang]
+  __shared__ double red[256];
+  const int cell = blockIdx.x;
+  for (int k = threadIdx.x; k < 6 * ng; k += blockDim.x) c[k] = raw[(size_t)cell * 6 * ng + k];
+  for (int k = threadIdx.x; k < nang; k += blockDim.x) f11[k] = F[(size_t)cell * nrow * nang + k];
+  __syncthreads();
+  double err = 0.0;
+  for (int e = threadIdx.x; e < 2 * nang; e += blockDim.x) {
+    const int which = e / nang, i = e % nang;
+    const GsfAlt a = alt[i];
+    double out[6];
+    gsf_matr_angle(ng, c, which ? a.ualt : a.u, out);
+    double ref;
+    if (which == 0) {
+      ref = f11[i];
+      if (fout)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) fout[((size_t)cell * 6 + k) * nang + i] = out[k];
+    } else {
+      const double y0 = f11[a.i0], y1 = f11[a.i1];
+      ref = __dadd_rn(__dmul_rn(__ddiv_rn(__dsub_rn(y1, y0), a.dx), a.num), y0);   // F11ALT(i), LINTERPOL in degrees
+    }
+    if (a.inrange) err = fmax(err, fabs(__dsub_rn(ref, out[0])));
+  }
+  red[threadIdx.x] = err;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + o]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && fiterr) fiterr[cell] = red[0];
+}
+
+int gsf_upload_alt(gm_handle_t h, int nang, const double* ang) {
+  const double PI = acos(-1.0), D2R = PI / 180.0;
+  const double ang_min = 0.0 * D2R, ang_max = 180.0 * D2R;   // params.h:9-10
+  std::vector<double> altd(nang);
+  altd[0] = ang[0];
+  altd[nang - 1] = ang[nang - 1];
+  for (int i = 2; i <= nang / 2; ++i) altd[i - 1] = 0.5 * (ang[i - 2] + ang[i - 1]);
+  for (int i = nang / 2 + 1; i <= nang - 1; ++i) altd[i - 1] = 0.5 * (ang[i] + ang[i - 1]);
+  std::vector<GsfAlt> A(nang);
+  for (int i = 0; i < nang; ++i) {
+    const double x = altd[i];
+    GsfAlt& a = A[i];
+    if (x < ang[0]) {
+      a.i0 = 0; a.i1 = 1; a.dx = ang[1] - ang[0]; a.num = x - ang[0];
+    } else if (x > ang[nang - 1]) {
+      a.i0 = nang - 2; a.i1 = nang - 1; a.dx = ang[nang - 1] - ang[nang - 2]; a.num = x - ang[nang - 2];
+    } else {
+      int I;
+      for (I = 2; I <= nang; ++I)
+        if (ang[I - 1] > x) break;
+      if (I > nang) I = nang;
+      a.i0 = I - 2; a.i1 = I - 1; a.dx = ang[I - 1] - ang[I - 2]; a.num = x - ang[I - 2];
+    }
+    const double r = ang[i] * D2R;
+    a.u = cos(r);
+    a.ualt = cos(altd[i] * D2R);
+    a.inrange = !(r < ang_min || r > ang_max);
+    a.pad = 0;
+  }
+  int rc = h->gsf_alt.ensure(sizeof(GsfAlt) * nang);
+  if (rc) return rc;
+  GM_CUDA_TRY(cudaMemcpyAsync(h->gsf_alt.p, A.data(), sizeof(GsfAlt) * nang, cudaMemcpyHostToDevice, h->stream));
+  GM_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return GM_OK;
 }
 
 int gsf_upload_constants(gm_handle_t h, int nang, const double* h_ang_deg, int ng) {
@@ -222,10 +359,11 @@ int gsf_upload_constants(gm_handle_t h, int nang, const double* h_ang_deg, int n
 }
 
 int gsf_core(gm_handle_t h, int ncell, int nang, const double* h_ang_deg, const double* d_F, int ng, double* d_coef,
-             double* d_cnorm, int quantize10, int nrow = 6) {
+             double* d_cnorm, int quantize10, int nrow = 6, double* d_fout = nullptr, double* d_fiterr = nullptr) {
   GM_REQUIRE(ng >= 3 && ng <= 2048, "ng out of range");
   GM_REQUIRE(nang >= 2 && nang <= 1000, "nang out of range (NANG_MAX = 1000, params.h:1)");
   cudaStream_t st = h->stream;
+  const bool diag = d_fout || d_fiterr;
   // the constants depend only on (ng, angle grid): build and upload them once per grid
   std::vector<double> key(h_ang_deg, h_ang_deg + nang);
   key.push_back((double)ng);
@@ -233,11 +371,29 @@ int gsf_core(gm_handle_t h, int ncell, int nang, const double* h_ang_deg, const 
     int rc0 = gsf_upload_constants(h, nang, h_ang_deg, ng);
     if (rc0) return rc0;
     h->gsf_key = key;
+    h->gsf_alt_valid = false;
+  }
+  double* d_raw = nullptr;
+  if (diag) {
+    int rc0;
+    if (!h->gsf_alt_valid) {
+      if ((rc0 = gsf_upload_alt(h, nang, h_ang_deg))) return rc0;
+      h->gsf_alt_valid = true;
+    }
+    if ((rc0 = h->gsf_raw.ensure(sizeof(double) * (size_t)ncell * 6 * ng))) return rc0;
+    d_raw = h->gsf_raw.as<double>();
   }
   const size_t smem = sizeof(double) * (6 * (size_t)nang + 12 * (size_t)ng);
   GM_CUDA_TRY(cudaFuncSetAttribute(k_gsf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_gsf<<<ncell, 256, smem, st>>>(nrow, nang, ng, d_F, h->gsf_nodes.as<GsfNode>(), h->gsf_table.as<double>(), d_coef, d_cnorm, quantize10);
+  k_gsf<<<ncell, 256, smem, st>>>(nrow, nang, ng, d_F, h->gsf_nodes.as<GsfNode>(), h->gsf_table.as<double>(), d_coef, d_cnorm, quantize10,
+                                  d_raw);
   GM_LAUNCH_CHECK(h);
+  if (diag) {
+    const size_t smem2 = sizeof(double) * (6 * (size_t)ng + (size_t)nang);
+    GM_CUDA_TRY(cudaFuncSetAttribute(k_gsf_matr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    k_gsf_matr<<<ncell, 256, smem2, st>>>(nrow, nang, ng, d_F, d_raw, h->gsf_alt.as<GsfAlt>(), d_fout, d_fiterr);
+    GM_LAUNCH_CHECK(h);
+  }
   return GM_OK;
 }
 
@@ -280,6 +436,41 @@ extern "C" int gm_gsf_expand(gm_handle_t h, int ncell, int nang, const double* a
   if (rc) return rc;
   GM_CUDA_TRY(cudaMemcpyAsync(coef, h->ws[3].p, sizeof(double) * nc, cudaMemcpyDeviceToHost, st));
   if (cnorm) GM_CUDA_TRY(cudaMemcpyAsync(cnorm, h->ws[4].p, sizeof(double) * ncell, cudaMemcpyDeviceToHost, st));
+  GM_CUDA_TRY(cudaStreamSynchronize(st));
+  return GM_OK;
+}
+
+extern "C" int gm_gsf_diagnose_dev(gm_handle_t h, int ncell, int nang, const double* ang_deg, const double* F, int nrow, int ng,
+                                   double* coef, double* cnorm, int quantize10, double* fout, double* fiterr) {
+  GM_REQUIRE(h && ang_deg && F && coef, "NULL argument");
+  GM_REQUIRE(ncell > 0, "ncell must be > 0");
+  GM_REQUIRE(nrow == 6 || nrow == 4, "nrow must be 6 (F11,F22,F33,F44,F12,F34) or 4 (P11,P12,P33,P34)");
+  GM_REQUIRE(fout || fiterr, "give fout and/or fiterr (use gm_gsf_expand_dev for the moments alone)");
+  GM_CUDA_TRY(cudaSetDevice(h->device));
+  return gsf_core(h, ncell, nang, ang_deg, F, ng, coef, cnorm, quantize10, nrow, fout, fiterr);
+}
+
+extern "C" int gm_gsf_diagnose(gm_handle_t h, int ncell, int nang, const double* ang_deg, const double* F, int ng, double* coef,
+                               double* cnorm, int quantize10, double* fout, double* fiterr) {
+  GM_REQUIRE(h && ang_deg && F && coef, "NULL argument");
+  GM_REQUIRE(ncell > 0, "ncell must be > 0");
+  GM_REQUIRE(fout || fiterr, "give fout and/or fiterr (use gm_gsf_expand for the moments alone)");
+  GM_CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  int rc;
+  const size_t nf = (size_t)ncell * 6 * nang, nc = (size_t)ncell * 6 * ng;
+  if ((rc = h->ws[2].ensure(sizeof(double) * nf)) || (rc = h->ws[3].ensure(sizeof(double) * nc)) ||
+      (rc = h->ws[4].ensure(sizeof(double) * ncell)) || (rc = h->ws[5].ensure(sizeof(double) * nf)) ||
+      (rc = h->ws[6].ensure(sizeof(double) * ncell)))
+    return rc;
+  GM_CUDA_TRY(cudaMemcpyAsync(h->ws[2].p, F, sizeof(double) * nf, cudaMemcpyHostToDevice, st));
+  rc = gsf_core(h, ncell, nang, ang_deg, h->ws[2].as<double>(), ng, h->ws[3].as<double>(), h->ws[4].as<double>(), quantize10, 6,
+                h->ws[5].as<double>(), h->ws[6].as<double>());
+  if (rc) return rc;
+  GM_CUDA_TRY(cudaMemcpyAsync(coef, h->ws[3].p, sizeof(double) * nc, cudaMemcpyDeviceToHost, st));
+  if (cnorm) GM_CUDA_TRY(cudaMemcpyAsync(cnorm, h->ws[4].p, sizeof(double) * ncell, cudaMemcpyDeviceToHost, st));
+  if (fout) GM_CUDA_TRY(cudaMemcpyAsync(fout, h->ws[5].p, sizeof(double) * nf, cudaMemcpyDeviceToHost, st));
+  if (fiterr) GM_CUDA_TRY(cudaMemcpyAsync(fiterr, h->ws[6].p, sizeof(double) * ncell, cudaMemcpyDeviceToHost, st));
   GM_CUDA_TRY(cudaStreamSynchronize(st));
   return GM_OK;
 }

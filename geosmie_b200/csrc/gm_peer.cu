@@ -98,3 +98,26 @@ extern "C" int gm_peer_sync(gm_handle_t h) {
   h->peer_pending = false;
   return GM_OK;
 }
+
+// Marks: gm_peer_mark(i) records "every put issued so far" on the exchange stream; gm_peer_wait(i) makes the compute stream
+// wait for that point -- the fence a double-buffered producer needs before it overwrites the source of an earlier put,
+// without giving up the overlap of the most recent one.  A mark that was never recorded does not block.
+extern "C" int gm_peer_mark(gm_handle_t h, int idx) {
+  GM_REQUIRE(h != nullptr, "handle is NULL");
+  GM_REQUIRE(idx >= 0 && idx < 4, "mark index out of range (0..3)");
+  GM_CUDA_TRY(cudaSetDevice(h->device));
+  int rc = peer_streams(h);
+  if (rc) return rc;
+  if (!h->peer_marks[idx]) GM_CUDA_TRY(cudaEventCreateWithFlags(&h->peer_marks[idx], cudaEventDisableTiming));
+  GM_CUDA_TRY(cudaEventRecord(h->peer_marks[idx], h->peer_stream));
+  return GM_OK;
+}
+
+extern "C" int gm_peer_wait(gm_handle_t h, int idx) {
+  GM_REQUIRE(h != nullptr, "handle is NULL");
+  GM_REQUIRE(idx >= 0 && idx < 4, "mark index out of range (0..3)");
+  if (!h->peer_marks[idx]) return GM_OK;
+  GM_CUDA_TRY(cudaSetDevice(h->device));
+  GM_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->peer_marks[idx], 0));
+  return GM_OK;
+}

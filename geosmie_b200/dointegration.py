@@ -238,8 +238,11 @@ def postprocess(ret, ang):
     theta = np.radians(ang)
     p11 = ret['p11']
     p11n = 2. * p11 / _trapz(p11 * np.sin(theta), theta)[..., None]
-    for k in ('p12', 'p22', 'p33', 'p34', 'p44'):
+    same44 = ret['p44'] is ret['p33'] or np.array_equal(ret['p44'], ret['p33'])
+    for k in ('p12', 'p22', 'p33', 'p34'):
         ret[k] = ret[k] * p11n / p11
+    # spheres: p44 == p33 on input (calculateScatVals), so the same arithmetic gives the same bits -- evaluated once
+    ret['p44'] = ret['p33'].copy() if same44 else ret['p44'] * p11n / p11
     ret['p11'] = p11n
     ret['pback'] = np.stack([ret[k][..., -1] for k in ('p11', 'p12', 'p33', 'p34', 'p22', 'p44')], axis=-1)
     return ret

@@ -60,8 +60,28 @@ def getWaterM():
     return data
 
 
+_growth_memo = {}
+
+
 def humidityGrowth(params, siz0, rh, allrh):
-    """Humidified size of a dry size siz0 at relative humidity rh (particleparams.py:85-108)."""
+    """Humidified size of a dry size siz0 at relative humidity rh (particleparams.py:85-108).  The result does not depend
+    on the wavelength, while the table build asks for it in every (wavelength, RH) cell: memoised per (params object, dry
+    size, RH) -- same arithmetic, evaluated once."""
+    key = (id(params), siz0, rh)
+    try:
+        hit = _growth_memo.get(key)
+    except TypeError:          # unhashable size (array): no memo
+        return _humidityGrowth(params, siz0, rh, allrh)
+    if hit is not None and hit[0] is params and hit[1] is allrh:
+        return hit[2]
+    val = _humidityGrowth(params, siz0, rh, allrh)
+    if len(_growth_memo) > 65536:
+        _growth_memo.clear()
+    _growth_memo[key] = (params, allrh, val)
+    return val
+
+
+def _humidityGrowth(params, siz0, rh, allrh):
     rhi = list(allrh).index(rh)
     rhtype = params['type']
     rhp = params['params']

@@ -13,6 +13,7 @@
 #ifndef GEOSMIE_B200_H
 #define GEOSMIE_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -187,6 +188,17 @@ int gm_gsf_expand_dev(gm_handle_t h, int ncell, int nang, const double* ang_deg,
 int gm_gsf_expand_phase4_dev(gm_handle_t h, int ncell, int nang, const double* ang_deg, const double* P4, int ng, double* coef,
                              double* cnorm, int quantize10);
 
+/* The diagnostic half of the same program: the matrix re-synthesised from the UN-normalised coefficients at the input angles
+ * (MATR, spher_expan.f:419-517 -- what main writes to <file>.expan_matr, :84-90) and the fit error one_calc returns and main
+ * prints (:168-177): fiterr = max |F11 - F11OUT| (ERREVAL :636-688 with ERRTYP = MAXABS over [0, 180] deg, params.h:8-10) over
+ * the input grid and READMATRIX's alternative (mid-point) grid (:237-258, USE_ALT_ANG = 1).  The moments are returned as by
+ * gm_gsf_expand.  fout [ncell][6][nang] (order F11,F22,F33,F44,F12,F34; nullable), fiterr [ncell] (nullable; not both NULL).
+ * The _dev variant also accepts gm_table_run's 4-row phase layout (nrow = 4). */
+int gm_gsf_diagnose(gm_handle_t h, int ncell, int nang, const double* ang_deg, const double* F, int ng, double* coef,
+                    double* cnorm, int quantize10, double* fout, double* fiterr);
+int gm_gsf_diagnose_dev(gm_handle_t h, int ncell, int nang, const double* ang_deg, const double* F, int nrow, int ng,
+                        double* coef, double* cnorm, int quantize10, double* fout, double* fiterr);
+
 /* ---- B5: band averaging ----------------------------------------------------------------------------------------------
  * Replaces bandaverage.doAverage (src/geosmie/bandaverage.py:18-50) over all (variable, bin, rh) columns.
  *   v [ncol][nlam] at wavelengths lam[nlam] (metres, ascending); bands lo/hi [nband] in cm^-1 (use_wavenum=1) or metres
@@ -211,6 +223,8 @@ int gm_band_average(gm_handle_t h, int ncol, int nlam, const double* lam, const 
  *                 the given (peer) pointers, [ntask][nmode][GM_NSCAL] and [ntask][4][nang], so the transfer is part of the
  *                 producing kernel (P2P stores over NVLink) and needs no extra pass; gm_gsf_expand_phase4_dev accepts a
  *                 peer pointer for `coef` likewise.  NULL, NULL switches it off.
+ *   gm_peer_mark / gm_peer_wait   mark(i) remembers "all puts issued so far"; wait(i) makes the compute stream wait for that
+ *                 point (i = 0..3): the fence of a double-buffered producer before it overwrites the source of an older put.
  */
 #define GM_IPC_HANDLE_BYTES 64
 int gm_peer_alloc(gm_handle_t h, size_t bytes, void** dptr, unsigned char ipc_handle[GM_IPC_HANDLE_BYTES]);
@@ -220,6 +234,8 @@ int gm_peer_close(gm_handle_t h, void* dptr);
 int gm_peer_put(gm_handle_t h, void* dst, const void* src, size_t bytes);
 int gm_peer_join(gm_handle_t h);
 int gm_peer_sync(gm_handle_t h);
+int gm_peer_mark(gm_handle_t h, int idx);
+int gm_peer_wait(gm_handle_t h, int idx);
 int gm_table_set_mirror(gm_table_t t, double* scal_mirror, double* phase_mirror);
 
 #ifdef __cplusplus

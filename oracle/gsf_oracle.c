@@ -90,15 +90,11 @@ static void gener(double U, int L1MAX, const double* const* CO, double D6, doubl
 }
 
 /*
- * one_calc (spher_expan.f:120-180) + SPHER_EXPAN (:269-358) + the normalisation/output block of main (:93-107).
- *   ang_deg[nang], F[6][nang] in the order F11,F22,F33,F44,F12,F34 (convertncdf.py:177);
- *   coef[6][ng] = AL1,AL2,AL3,AL4,BET1,BET2 (times CNORM); returns CNORM = 1/AL1(1).
- *   quantize10 != 0 rounds to 10 decimals like the '(X,I5,6F17.10)' record (:96,:104).
+ * The expansion itself: one_calc's interpolation to the Gauss nodes (spher_expan.f:158-167) + SPHER_EXPAN (:269-358).
+ *   angl[nang] in radians, F[6][nang] in the order F11,F22,F33,F44,F12,F34 (convertncdf.py:177);
+ *   raw[6][ng] = AL1,AL2,AL3,AL4,BET1,BET2 as SPHER_EXPAN leaves them (NOT yet multiplied by CNORM).
  */
-double orc_gsf_expand(int nang, const double* ang_deg, const double* F, int ng, double* coef, int quantize10) {
-  const double PI = acos(-1.0), D2R = PI / 180.0;      /* params.h:3-4 */
-  double* angl = (double*)malloc(sizeof(double) * nang);
-  for (int i = 0; i < nang; ++i) angl[i] = ang_deg[i] * D2R;   /* READMATRIX :260-263 */
+static void gsf_raw(int nang, const double* angl, const double* F, int ng, double* raw) {
   int NG = ng, L1MAX = ng;
   double* X = (double*)malloc(sizeof(double) * NG * 2);
   double* W = X + NG;
@@ -151,16 +147,77 @@ double orc_gsf_expand(int nang, const double* ang_deg, const double* F, int ng, 
     BET1[L1] *= CL;
     BET2[L1] *= CL;
   }
-  double CNORM = 1.0 / AL1[1];                          /* main :95 */
   double* S[6] = {AL1, AL2, AL3, AL4, BET1, BET2};
   for (int k = 0; k < 6; ++k)
-    for (int L1 = 1; L1 <= L1MAX; ++L1) {
-      double v = S[k][L1] * CNORM;
+    for (int L1 = 1; L1 <= L1MAX; ++L1) raw[(size_t)k * ng + (L1 - 1)] = S[k][L1];
+  free(buf); free(FN); free(X);
+}
+
+/*
+ * one_calc (spher_expan.f:120-180) + SPHER_EXPAN (:269-358) + the normalisation/output block of main (:93-107).
+ *   ang_deg[nang], F[6][nang] in the order F11,F22,F33,F44,F12,F34 (convertncdf.py:177);
+ *   coef[6][ng] = AL1,AL2,AL3,AL4,BET1,BET2 (times CNORM); returns CNORM = 1/AL1(1).
+ *   quantize10 != 0 rounds to 10 decimals like the '(X,I5,6F17.10)' record (:96,:104).
+ */
+double orc_gsf_expand(int nang, const double* ang_deg, const double* F, int ng, double* coef, int quantize10) {
+  const double PI = acos(-1.0), D2R = PI / 180.0;      /* params.h:3-4 */
+  double* angl = (double*)malloc(sizeof(double) * nang);
+  for (int i = 0; i < nang; ++i) angl[i] = ang_deg[i] * D2R;   /* READMATRIX :260-263 */
+  double* raw = (double*)malloc(sizeof(double) * 6 * ng);
+  gsf_raw(nang, angl, F, ng, raw);
+  double CNORM = 1.0 / raw[0];                          /* main :95 */
+  for (int k = 0; k < 6; ++k)
+    for (int l = 0; l < ng; ++l) {
+      double v = raw[(size_t)k * ng + l] * CNORM;
       if (quantize10) v = rint(v * 1e10) / 1e10;
-      coef[(size_t)k * ng + (L1 - 1)] = v;
+      coef[(size_t)k * ng + l] = v;
     }
-  free(buf); free(FN); free(X); free(angl);
+  free(raw); free(angl);
   return CNORM;
+}
+
+void orc_gsf_matr(int ng, const double* coef, int nang, const double* angl_rad, double* out);
+
+/*
+ * The diagnostic half of the program: READMATRIX's alternative angle grid (:235-258, USE_ALT_ANG = 1, params.h:13),
+ * one_calc's two MATR + ERREVAL calls (:168-177; ERRTYP = MAXABS over [ang_min, ang_max] = [0, 180] deg, params.h:8-10)
+ * and what main writes to <file>.expan_matr (:84-90): the matrix re-synthesised from the UN-normalised coefficients at the
+ * input angles.  fout[6][nang] = F11OUT,F22OUT,F33OUT,F44OUT,F12OUT,F34OUT; returns fiterr.
+ */
+double orc_gsf_one_calc(int nang, const double* ang_deg, const double* F, int ng, double* fout) {
+  const double PI = acos(-1.0), D2R = PI / 180.0;
+  const double ang_min = 0.0 * D2R, ang_max = 180.0 * D2R;
+  double* angl = (double*)malloc(sizeof(double) * nang * 4);
+  double* alt = angl + nang, *f11alt = alt + nang, *tmp = f11alt + nang;
+  /* READMATRIX: alternative grid and F11ALT, both still in degrees (:237-251; 1-based i) */
+  alt[0] = ang_deg[0];
+  alt[nang - 1] = ang_deg[nang - 1];
+  for (int i = 2; i <= nang / 2; ++i) alt[i - 1] = 0.5 * (ang_deg[i - 2] + ang_deg[i - 1]);
+  for (int i = nang / 2 + 1; i <= nang - 1; ++i) alt[i - 1] = 0.5 * (ang_deg[i] + ang_deg[i - 1]);
+  for (int i = 0; i < nang; ++i) f11alt[i] = orc_linterpol(nang, ang_deg, F, alt[i]);
+  for (int i = 0; i < nang; ++i) {                      /* :260-263 */
+    angl[i] = ang_deg[i] * D2R;
+    alt[i] = alt[i] * D2R;
+  }
+  double* raw = (double*)malloc(sizeof(double) * 6 * ng);
+  gsf_raw(nang, angl, F, ng, raw);
+  double* out = (double*)malloc(sizeof(double) * 6 * nang);
+  double err_alt = 0.0, err = 0.0;
+  orc_gsf_matr(ng, raw, nang, alt, out);                /* :169 */
+  for (int i = 0; i < nang; ++i) {                      /* ERREVAL(NANG,angl,F11ALT,F11OUT,...), :170: range test on angl */
+    if (angl[i] < ang_min || angl[i] > ang_max) continue;
+    double t = fabs(f11alt[i] - out[i]);
+    if (t > err_alt) err_alt = t;
+  }
+  orc_gsf_matr(ng, raw, nang, angl, fout);              /* :173 */
+  for (int i = 0; i < nang; ++i) {
+    if (angl[i] < ang_min || angl[i] > ang_max) continue;
+    double t = fabs(F[i] - fout[i]);
+    if (t > err) err = t;
+  }
+  (void)tmp;
+  free(out); free(raw); free(angl);
+  return err > err_alt ? err : err_alt;                 /* :176 */
 }
 
 /*

@@ -20,6 +20,7 @@ def lib():
             subprocess.check_call(["make", "-s", "-C", _HERE])
         L = C.CDLL(path)
         L.orc_gsf_expand.restype = C.c_double
+        L.orc_gsf_one_calc.restype = C.c_double
         _LIB = L
     return _LIB
 
@@ -51,3 +52,14 @@ def matr(coef, ang_deg):
     out = np.zeros((6, ang.size))
     lib().orc_gsf_matr(C.c_int(coef.shape[1]), _p(coef), C.c_int(ang.size), _p(ang), _p(out))
     return out
+
+
+def one_calc(ang_deg, F, ng=129):
+    """The diagnostic half of spher_expan.f (alternative angle grid, MATR, ERREVAL): F [6][nang] ->
+    (fout [6][nang] = the .expan_matr columns, fiterr)."""
+    ang = np.ascontiguousarray(ang_deg, dtype=float)
+    F = np.ascontiguousarray(F, dtype=float)
+    assert F.shape == (6, ang.size)
+    out = np.zeros((6, ang.size))
+    err = lib().orc_gsf_one_calc(C.c_int(ang.size), _p(ang), _p(F), C.c_int(ng), _p(out))
+    return out, float(err)

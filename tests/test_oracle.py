@@ -140,3 +140,46 @@ def test_gsf_matr_round_trip():
     assert np.max(np.abs(back - F2)) / np.abs(F2).max() < 5e-4
     q = go.expand(ang, F2, quantize10=True)[0]
     assert np.max(np.abs(q - coef)) <= 0.5e-10 + 1e-15
+
+
+def test_gsf_one_calc_diagnostics():
+    """one_calc's fit error (spher_expan.f:168-177): the alternative (mid-point) angle grid of READMATRIX :237-258, MATR on the
+    un-normalised coefficients and ERREVAL (MAXABS).  Rayleigh is reproduced to the linear-interpolation limit of the grid;
+    a matrix that 129 terms cannot represent (a step) must give a large error."""
+    ang = table_angles()
+    F = rayleigh(ang)
+    fout, err = go.one_calc(ang, F)
+    coef, cn = go.expand(ang, F)
+    assert np.max(np.abs(fout - go.matr(coef / cn, ang))) < 1e-12           # same re-synthesis up to the CNORM round trip
+    assert np.max(np.abs(fout[0] - F[0])) <= err < 1e-4
+    # the alt grid only matters when the error between the nodes is larger than at the nodes
+    uni = np.linspace(0., 180., 181)
+    Fu = rayleigh(uni)
+    _, err_u = go.one_calc(uni, Fu)
+    assert err_u < 2e-4
+    step = Fu.copy()
+    step[0, 60:] += 1.0
+    _, err_s = go.one_calc(uni, step)
+    assert err_s > 0.05
+
+
+def test_fortran_edit_descriptors():
+    """Formats of <file>.expan_coeff '(X,I5,6F17.10)' and <file>.expan_matr '(F6.2,X,4E15.5,2F11.5)', spher_expan.f:84-107."""
+    from geosmie_b200.gsf import spher_expan as se
+    assert se.fortran_e(1.0, 15, 5) == "    0.10000E+01"
+    assert se.fortran_e(-0.00123456, 15, 5) == "   -0.12346E-02"
+    assert se.fortran_e(0.0, 15, 5) == "    0.00000E+00"
+    assert se.fortran_e(9.99999e4, 15, 5) == "    0.10000E+06"      # rounding carries into the exponent
+    assert se.fortran_e(1.5e-120, 15, 5) == "    0.15000-119"       # three-digit exponents drop the 'E'
+    assert se.fortran_f(180.0, 6, 2) == "180.00" and se.fortran_f(0.5, 6, 2) == "  0.50"
+    assert se.fortran_f(-0.75, 11, 5) == "   -0.75000" and se.fortran_f(1e7, 6, 2) == "******"
+    coef = np.arange(12, dtype=float).reshape(6, 2) / 7.0
+    txt = se.format_expan_coeff(coef, 0.999987)
+    rows = txt.splitlines()
+    assert rows[0] == "     1     0.9999870000" and len(rows) == 3 and len(rows[1]) == 6 + 6 * 17
+    # the reference's consumer: np.loadtxt(skiprows=1, unpack=True), columns 1..6 (convertncdf.py:189, :381-394)
+    import io
+    back = np.loadtxt(io.StringIO(txt), skiprows=1, unpack=True)
+    assert back.shape == (7, 2) and np.max(np.abs(back[1:] - coef)) <= 0.5e-10
+    m = se.format_expan_matr(np.array([0.0, 90.0, 180.0]), np.ones((6, 3)))
+    assert m.splitlines()[2] == "180.00" + " " + "    0.10000E+01" * 4 + "    1.00000" * 2
