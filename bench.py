@@ -57,7 +57,7 @@ def flop_model(nmax, nmx_sum, ncell_factor=1):
     `survey`:   the SURVEY 8d model F(p) = nmax (16 N_ang + 94) + 14 nmx + 22 N_ang (the reference's four complex dots);
     `gram`:     the Gram formulation (k_gram): four N x N blocks, K = 2 per particle -> 16 nmax^2 flop per particle, no
                 tile padding counted;
-    `gram_exec`: the DMMA flop k_gram actually issues (8-row tiles, classes 5 -> 6 and 7 -> 8 tiles, full symmetric blocks);
+    `gram_exec`: the DMMA flop k_gram actually issues (8-row tiles, full symmetric blocks, stacked tile for nmax <= 4);
     `coeff`:    14 nmx + 94 nmax per particle (recurrences, a_n, b_n, efficiencies)."""
     nm = np.asarray(nmax, dtype=np.float64)
     snm = float(nm.sum()) * ncell_factor
@@ -67,13 +67,14 @@ def flop_model(nmax, nmx_sum, ncell_factor=1):
     pad[:len(nm)] = nm
     gm = pad.reshape(ng, 32).max(axis=1)
     tg = np.ceil(gm / 8.0)
-    tg[tg == 5] = 6
-    tg[tg == 7] = 8
     in_gram = gm <= 64
+    # DMMAs k_gram issues per group of 32 particles (16 k-steps): stacked c+/c- tile when nmax <= 4 (2 per k-step), 4 tg^2 up
+    # to 4 tiles, 12 warps x tg x ceil((tg+2)/3) column tiles above (the ragged last third recomputes one tile)
+    dm = np.where(gm <= 4, 32.0, np.where(tg <= 4, 64.0 * tg * tg, 16.0 * 12.0 * tg * np.floor((tg + 2) / 3)))
     return {"contract": snm * 8.0 * NANG + npart * 16.0 * NANG,
             "survey": snm * (16.0 * NANG + 94.0) + 14.0 * nmx_sum + npart * 22.0 * NANG,
             "gram": 16.0 * float((nm[np.repeat(in_gram, 32)[:len(nm)]] ** 2).sum()) * ncell_factor,
-            "gram_exec": 512.0 * float((4.0 * tg[in_gram] ** 2 * 16.0).sum()) * ncell_factor,
+            "gram_exec": 512.0 * float(dm[in_gram].sum()) * ncell_factor,
             "coeff": 14.0 * nmx_sum + 94.0 * snm}
 
 

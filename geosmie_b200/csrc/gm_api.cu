@@ -112,7 +112,7 @@ struct Groups {
   std::vector<int> gk4, grow;    // DMMA k4 steps and first coefficient row of group g
   long long bessel_len = 0;      // doubles per Bessel table
   long long task_rows = 0;       // coefficient rows per task
-  // Gram path (gm_gram.cuh): groups with max nmax <= 64, listed class by class (class = number of 8-row tiles, 5 -> 6, 7 -> 8)
+  // Gram path (gm_gram.cuh): groups with max nmax <= 64, listed class by class (class = number of 8-row tiles; 0 = max nmax <= 4)
   std::vector<unsigned char> gskip;   // 1 = Gram group
   std::vector<int> glist;             // Gram groups ordered by class, ascending group index inside a class
   int cls_begin[GM_GRAM_MAX_TG + 2] = {0};   // glist range of class c: [cls_begin[c], cls_begin[c + 1])
@@ -120,10 +120,8 @@ struct Groups {
   int gram_tgmax = 0;                 // largest class present
   int ndirect = 0;                    // groups left to the per-angle contraction
   static int gram_class(int gm) {
-    int tg = (gm + 7) / 8;
-    if (tg == 5) tg = 6;
-    if (tg == 7) tg = 8;
-    return tg;
+    if (gm <= 4) return 0;      // stacked c+/c- tile (gm_gram.cuh, GramCfg<0>)
+    return (gm + 7) / 8;
   }
   void build_gram(const int32_t* nmax) {
     gskip.assign(ngroup, 0);
@@ -132,18 +130,17 @@ struct Groups {
     std::vector<int> gm(ngroup, 0);
     for (int g = 0; g < ngroup; ++g)
       for (int i = g * GM_GROUP; i < std::min(nx, (g + 1) * GM_GROUP); ++i) gm[g] = std::max(gm[g], (int)nmax[i]);
-    for (int c = 1; c <= GM_GRAM_MAX_TG; ++c) {
+    for (int c = 0; c <= GM_GRAM_MAX_TG; ++c) {
       cls_begin[c] = (int)glist.size();
       for (int g = 0; g < ngroup; ++g)
         if (gm[g] <= 8 * GM_GRAM_MAX_TG && gram_class(gm[g]) == c) {
           glist.push_back(g);
           gskip[g] = 1;
           gram_nmax = std::max(gram_nmax, gm[g]);
-          gram_tgmax = std::max(gram_tgmax, c);
+          gram_tgmax = std::max(gram_tgmax, std::max(c, 1));
         }
     }
     cls_begin[GM_GRAM_MAX_TG + 1] = (int)glist.size();
-    cls_begin[0] = 0;
     ndirect = ngroup - (int)glist.size();
   }
   void build(int n, const int32_t* nmax) {
@@ -592,17 +589,22 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
       P.item0 = (int)all_items.size();
       double ccost[GM_GRAM_MAX_TG + 1] = {0};
       double total = 0;
-      for (int c = 1; c <= GM_GRAM_MAX_TG; ++c) {
+      auto dmma_per_group = [](int c) {   // DMMAs a team issues per group (16 k-steps)
+        if (c == 0) return 32.0;
+        if (c <= 4) return 64.0 * c * c;
+        return 16.0 * 12.0 * c * ((c + 2) / 3);   // 12 warps x NI x CW tiles (ragged last third recomputes a tile)
+      };
+      for (int c = 0; c <= GM_GRAM_MAX_TG; ++c) {
         const int nc = G.cls_begin[c + 1] - G.cls_begin[c];
-        ccost[c] = (double)nc * (64.0 * c * c + 48.0);   // DMMA issue slots per task (+ ring handling per group)
+        ccost[c] = (double)nc * (dmma_per_group(c) + 48.0);   // DMMA issue slots per task (+ ring handling per group)
         total += ccost[c] * nt;
       }
       const double target = std::max(total / (h->sm_count * 6.0), 12000.0);
       std::vector<std::pair<double, GramItem>> items;
-      for (int c = 1; c <= GM_GRAM_MAX_TG; ++c) {
+      for (int c = 0; c <= GM_GRAM_MAX_TG; ++c) {
         const int nc = G.cls_begin[c + 1] - G.cls_begin[c];
         if (nc == 0) continue;
-        const int nteam = c == 1 ? 12 : c == 2 ? 6 : c <= 4 ? 3 : 1;   // GramCfg<c>::NTEAM
+        const int nteam = c <= 1 ? 12 : c == 2 ? 6 : c <= 4 ? 3 : 1;   // GramCfg<c>::NTEAM
         int nsplit = 1, tpc = 1;
         if (ccost[c] > 1.5 * target) nsplit = std::min(nc, (int)std::lround(ccost[c] / target));
         else tpc = std::max(1, std::min(nt, (int)(target / ccost[c])));
@@ -614,7 +616,7 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
           d.gbegin = G.cls_begin[c] + (int)((long long)nc * k / nsplit);
           d.gend = G.cls_begin[c] + (int)((long long)nc * (k + 1) / nsplit);
           d.hoff = P.hstride;
-          P.hstride += (long long)nteam * 4 * 64 * c * c;
+          P.hstride += (long long)nteam * 4 * (c == 0 ? 16 : 64 * c * c);   // GramCfg<c>::ND squared per block
           const int di = (int)all_desc.size() - P.desc0;
           all_desc.push_back(d);
           for (int t0 = 0; t0 < nt; t0 += tpc) {

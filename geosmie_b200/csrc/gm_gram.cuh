@@ -25,12 +25,12 @@
 
 constexpr int GM_GRAM_MAX_TG = 8;                                    // groups with max nmax <= 64 take the Gram path
 constexpr int GM_GRAM_THREADS = (GM_CONTRACT_WARPS + 1) * 32;        // 12 consumer warps + 1 producer warp
-constexpr int GM_GRAM_MAX_SLOTS = 24;
-constexpr int GM_GRAM_RING_DBL = GM_GRAM_MAX_SLOTS * 8 * GM_SB;      // 202 752 B
+constexpr int GM_GRAM_MAX_SLOTS = 48;
+constexpr int GM_GRAM_RING_DBL = 24 * 8 * GM_SB;                     // 202 752 B
 constexpr int GM_GRAM_SMEM = GM_GRAM_RING_DBL * 8 + 2 * GM_GRAM_MAX_SLOTS * 8 + GM_GRAM_MAX_SLOTS * 4 + 64 * 4;
 
 struct GramDesc {
-  int tg;          // template class: 1, 2, 3, 4, 6 or 8 tiles
+  int tg;          // template class: 1..8 tiles, 0 = stacked c+/c- tile of groups with nmax <= 4
   int nteam;       // teams writing separate partials
   int gbegin, gend;  // range in glist
   long long hoff;  // offset (doubles) of this descriptor's partials inside a task's partial-H block
@@ -53,17 +53,23 @@ struct GramArgs {
   long long hstride;
 };
 
+// TG = number of 8-row DMMA tiles of the class (1..8); TG = 0 is the STACKED class of groups with max nmax <= 4: rows 0-3 of
+// the single 8-row tile hold c+ of orders 1..4 and rows 4-7 hold c- (Y = [X+; X-]), so that ONE product Y Y^T delivers H1
+// (top-left 4 x 4), H3 (top-right) and H2 (bottom-right) and a second one, [X~+; 0] Y^T, delivers H4: 2 DMMAs per k-step
+// instead of the 4 of class 1 (over half of the optics_SU groups are in this class).
 template <int TG>
 struct GramCfg {
-  static constexpr int S = TG == 1 ? 1 : TG == 2 ? 2 : TG <= 4 ? 4 : 12;   // warps per team
+  static constexpr int TGE = TG == 0 ? 1 : TG;                                  // tiles per side
+  static constexpr int S = TG <= 1 ? 1 : TG == 2 ? 2 : TG <= 4 ? 4 : 12;        // warps per team
   static constexpr int NTEAM = GM_CONTRACT_WARPS / S;
-  static constexpr int DEPTH = TG <= 4 ? 2 : TG == 6 ? 4 : 3;              // ring slots per team
+  static constexpr int DEPTH = TG == 0 ? 4 : TG <= 4 ? 2 : TG <= 6 ? 4 : 3;     // ring slots per team
   static constexpr int R = NTEAM * DEPTH;
-  static constexpr int SLOT_DBL = 8 * TG * GM_SB;
-  static constexpr int CW = (TG + 2) / 3;                                   // column tiles per warp when S == 12
-  static constexpr int NJOB = S == 1 ? 4 : S == 2 ? 2 : 1;
-  static constexpr int NI = TG;
-  static constexpr int NJ = S == 12 ? CW : TG;
+  static constexpr int SLOT_DBL = (TG == 0 ? 4 : 8 * TG) * GM_SB;
+  static constexpr int CW = (TG + 2) / 3;                                       // column tiles per warp when S == 12
+  static constexpr int NJOB = TG == 0 ? 2 : S == 1 ? 4 : S == 2 ? 2 : 1;
+  static constexpr int NI = TGE;
+  static constexpr int NJ = S == 12 ? CW : TGE;
+  static constexpr int ND = TG == 0 ? 4 : 8 * TG;                               // side of the partial Gram blocks written by a team
   static_assert(R <= GM_GRAM_MAX_SLOTS && R * SLOT_DBL <= GM_GRAM_RING_DBL, "ring does not fit");
 };
 
@@ -75,7 +81,7 @@ __device__ __forceinline__ void gram_cta(const GramArgs& A, const GramItem it, c
                                          uint64_t* empty, volatile int* tags, volatile int* cand) {
   using C = GramCfg<TG>;
   constexpr int S = C::S, NTEAM = C::NTEAM, DEPTH = C::DEPTH, R = C::R, SLOT_DBL = C::SLOT_DBL, NI = C::NI, NJ = C::NJ, NJOB = C::NJOB;
-  constexpr int N = 8 * TG;
+  constexpr int N = C::ND;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int lk = lane & 3, lr = lane >> 2;
 
@@ -147,7 +153,8 @@ __device__ __forceinline__ void gram_cta(const GramArgs& A, const GramItem it, c
     tilde = blk == 3;
   }
   const double sgn = (lk & 1) ? -1.0 : 1.0;
-  const int lane_off = lr * GM_SB + lk;
+  // stacked class: tile row lr = order (lr & 3) + 1 of c+ (lr < 4) or c- (lr >= 4, 64 doubles further in the coefficient row)
+  const int lane_off = TG == 0 ? (lr & 3) * GM_SB + (lr >> 2) * 64 + lk : lr * GM_SB + lk;
 
   double acc[NJOB][NI][NJ][2];
 #pragma unroll
@@ -165,7 +172,17 @@ __device__ __forceinline__ void gram_cta(const GramArgs& A, const GramItem it, c
     if (nr > 0) {
       const double* st = ring + (size_t)s * SLOT_DBL + lane_off;
       const int nrl = nr - lr;   // row 8 i + lr of the slot was copied iff 8 i < nrl (otherwise it is a zero row)
-      if constexpr (S == 1) {
+      if constexpr (TG == 0) {
+        const bool have = (lr & 3) < nr;
+#pragma unroll 4
+        for (int ks = 0; ks < 16; ++ks) {
+          const double y = have ? st[4 * ks] : 0.0;
+          const double yx = __shfl_xor_sync(0xffffffffu, y, 1);
+          const double yt = lr < 4 ? sgn * yx : 0.0;
+          dmma884(acc[0][0][0][0], acc[0][0][0][1], y, y);    // Y Y^T: H1 | H3 / . | H2
+          dmma884(acc[1][0][0][0], acc[1][0][0][1], yt, y);   // [X~+; 0] Y^T: . | H4
+        }
+      } else if constexpr (S == 1) {
 #pragma unroll 4
         for (int ks = 0; ks < 16; ++ks) {
           const double fp = 0 < nrl ? st[4 * ks] : 0.0, fm = 0 < nrl ? st[64 + 4 * ks] : 0.0;
@@ -221,8 +238,20 @@ __device__ __forceinline__ void gram_cta(const GramArgs& A, const GramItem it, c
     } else {
       // end of task: this team's partial H -> global (fixed slot: summed in fixed order by k_gram_sum), then reset
       double* hp = A.hpart + (size_t)task * A.hstride + d.hoff + (size_t)team * 4 * N * N;
+      if constexpr (TG == 0) {
+        // 4 x 4 blocks: lane (lr, lk) holds rows lr, columns 2 lk, 2 lk + 1 of the two 8 x 8 products
+        const int r4 = lr & 3, c4 = 2 * (lk & 1);
+        const double2 g = make_double2(acc[0][0][0][0], acc[0][0][0][1]), tq = make_double2(acc[1][0][0][0], acc[1][0][0][1]);
+        if (lr < 4 && lk < 2) *reinterpret_cast<double2*>(hp + (0 * 4 + r4) * 4 + c4) = g;      // H1
+        if (lr >= 4 && lk >= 2) *reinterpret_cast<double2*>(hp + (1 * 4 + r4) * 4 + c4) = g;    // H2
+        if (lr < 4 && lk >= 2) {
+          *reinterpret_cast<double2*>(hp + (2 * 4 + r4) * 4 + c4) = g;                          // H3
+          *reinterpret_cast<double2*>(hp + (3 * 4 + r4) * 4 + c4) = tq;                         // H4
+        }
+        acc[0][0][0][0] = acc[0][0][0][1] = acc[1][0][0][0] = acc[1][0][0][1] = 0.0;
+      }
 #pragma unroll
-      for (int q = 0; q < NJOB; ++q) {
+      for (int q = 0; q < (TG == 0 ? 0 : NJOB); ++q) {
         int b = blk;
         if (S == 1) b = q;
         if (S == 2) b = q == 0 ? (r ? 2 : 0) : (r ? 3 : 1);
@@ -255,10 +284,13 @@ __global__ void __launch_bounds__(GM_GRAM_THREADS, 1) k_gram(GramArgs A) {
   const GramItem it = A.items[blockIdx.x];
   const GramDesc d = A.desc[it.desc];
   switch (d.tg) {
+    case 0: gram_cta<0>(A, it, d, ring, full, empty, tags, cand); break;
     case 1: gram_cta<1>(A, it, d, ring, full, empty, tags, cand); break;
     case 2: gram_cta<2>(A, it, d, ring, full, empty, tags, cand); break;
     case 3: gram_cta<3>(A, it, d, ring, full, empty, tags, cand); break;
     case 4: gram_cta<4>(A, it, d, ring, full, empty, tags, cand); break;
+    case 5: gram_cta<5>(A, it, d, ring, full, empty, tags, cand); break;
+    case 7: gram_cta<7>(A, it, d, ring, full, empty, tags, cand); break;
     case 6: gram_cta<6>(A, it, d, ring, full, empty, tags, cand); break;
     default: gram_cta<8>(A, it, d, ring, full, empty, tags, cand); break;
   }
@@ -287,7 +319,7 @@ __global__ void __launch_bounds__(256) k_gram_sum(GramSumArgs A) {
   double2 s = make_double2(0.0, 0.0);
   for (int k = 0; k < A.ndesc; ++k) {
     const GramDesc d = A.desc[k];
-    const int Nd = 8 * d.tg;
+    const int Nd = d.tg ? 8 * d.tg : 4;   // class 0 (stacked, nmax <= 4) writes 4 x 4 blocks
     if (n < Nd && c < Nd) {
       const double2* p = reinterpret_cast<const double2*>(hp + d.hoff + ((size_t)b * Nd + n) * Nd + c);
       const size_t stride = (size_t)2 * Nd * Nd;   // 4 Nd^2 doubles per team
