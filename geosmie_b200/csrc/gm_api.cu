@@ -14,6 +14,14 @@
 #ifndef GM_HIO_MIN_BATCHES
 #define GM_HIO_MIN_BATCHES 3     // host-buffer calls: batches whose H2D / D2H copies are pipelined against the kernels (optics_SU e2e: 2 -> 3.92, 3 -> 3.72, 4 -> 3.87, 6 -> 4.1 ms)
 #endif
+#ifndef GM_GRAM_INTERLEAVE
+#define GM_GRAM_INTERLEAVE 1     // k_gram launch order: HBM-bound (class 0/1) work items interleaved with the pipe-bound ones
+#endif
+#ifndef GM_GRAM_SLOW0
+#define GM_GRAM_SLOW0 1.0        // cost weight of class 0 / class 1 work items relative to their DMMA count.  Alone they run at 0.42 / 0.56 of
+#define GM_GRAM_SLOW1 1.0        // the DMMA peak against 0.76-0.84 for the others (tools/gram_class_probe.py), but weighting them 1.85 / 1.4
+                                 // only made their task ranges shorter: optics_SU k_gram 1.249 ms against 1.197 ms (1.0 / 1.0)
+#endif
 #ifndef GM_EVAL_CTAS_PER_SM
 #define GM_EVAL_CTAS_PER_SM 2    // k_gram_eval: CTAs (angle block x task range) per SM
 #endif
@@ -594,9 +602,13 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
         if (c <= 4) return 64.0 * c * c;
         return 16.0 * 12.0 * c * ((c + 2) / 3);   // 12 warps x NI x CW tiles (ragged last third recomputes a tile)
       };
+      // Classes 0 and 1 read 132 B of coefficient stream per DMMA and are bound by HBM, not by the tensor pipe (measured alone:
+      // 0.42 / 0.56 of the DMMA peak at 4-5.4 TB/s, the others 0.76-0.84): they must not run all at the same time (see the
+      // interleaving below).
+      static const double slow[2] = {GM_GRAM_SLOW0, GM_GRAM_SLOW1};
       for (int c = 0; c <= GM_GRAM_MAX_TG; ++c) {
         const int nc = G.cls_begin[c + 1] - G.cls_begin[c];
-        ccost[c] = (double)nc * (dmma_per_group(c) + 48.0);   // DMMA issue slots per task (+ ring handling per group)
+        ccost[c] = (double)nc * (dmma_per_group(c) + 48.0) * (c <= 1 ? slow[c] : 1.0);   // DMMA issue slots per task (+ ring handling per group)
         total += ccost[c] * nt;
       }
       const double target = std::max(total / (h->sm_count * 6.0), 12000.0);
@@ -625,8 +637,29 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
           }
         }
       }
-      std::stable_sort(items.begin(), items.end(), [](const auto& a, const auto& b) { return a.first > b.first; });
-      for (auto& e : items) all_items.push_back(e.second);
+      // Launch order (the hardware hands out CTAs in index order as SMs become free): longest first inside each of two queues,
+      // the HBM-bound items (classes 0, 1) and the pipe-bound ones, merged so that both queues advance at the same relative
+      // pace -- at any moment only a fraction of the SMs streams small-class groups and the rest keeps the DMMA pipes busy.
+      std::vector<std::pair<double, GramItem>> q[2];
+      double qsum[2] = {0, 0};
+      for (auto& e : items) {
+        const int c = all_desc[P.desc0 + e.second.desc].tg;
+        const int w = (GM_GRAM_INTERLEAVE && c <= 1) ? 1 : 0;
+        q[w].push_back(e);
+        qsum[w] += e.first;
+      }
+      for (int w = 0; w < 2; ++w)
+        std::stable_sort(q[w].begin(), q[w].end(), [](const auto& a, const auto& b) { return a.first > b.first; });
+      size_t qi[2] = {0, 0};
+      double qdone[2] = {0, 0};
+      while (qi[0] < q[0].size() || qi[1] < q[1].size()) {
+        int w;
+        if (qi[0] >= q[0].size()) w = 1;
+        else if (qi[1] >= q[1].size()) w = 0;
+        else w = (qdone[1] / qsum[1] < qdone[0] / qsum[0]) ? 1 : 0;
+        qdone[w] += q[w][qi[w]].first;
+        all_items.push_back(q[w][qi[w]++].second);
+      }
       P.ndesc = (int)all_desc.size() - P.desc0;
       P.nitem = (int)all_items.size() - P.item0;
       plans.push_back(P);
