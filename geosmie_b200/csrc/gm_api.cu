@@ -742,7 +742,11 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
     A.gact = t->h->scratch_gact.as<unsigned char>();
     A.scal_part = t->h->scratch_scal_part.as<double>();
     A.q = d_q ? d_q + (size_t)t0 * G.nx * 6 : nullptr;
+#ifdef GM_NO_STATS
+    A.stats = nullptr;
+#else
     A.stats = t->stats.as<unsigned long long>();
+#endif
     const GramPlan* P = nullptr;
     for (auto& q : plans)
       if (q.nt == nt) P = &q;

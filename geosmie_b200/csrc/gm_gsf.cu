@@ -6,6 +6,7 @@
 //   device (one CTA per cell): interpolate the six elements to the nodes, weight, contract with the table
 //     (SPHER_EXPAN :304-347) in the Fortran accumulation order, normalise by AL1(0) (main :95-103).
 #include <math.h>
+#include <stdlib.h>
 
 #include "gm_common.cuh"
 
@@ -178,6 +179,101 @@ __global__ void __launch_bounds__(256) k_gsf(int nrow, int nang, int ng, const d
     }
   }
   if (threadIdx.x == 0 && cnorm) cnorm[cell] = cn;
+}
+
+// k_gsf_multi: the same arithmetic in the same order as k_gsf (bit-identical results), with GSF_CB cells per CTA.  k_gsf reads
+// the whole table of generalized spherical functions (4 x ng x ng doubles = 532 KB for ng = 129) through L1 once per cell and is
+// bound by L2 -> SM bandwidth (optics_SU: 1.2 GB per step).  Here every table value a thread loads is used for GSF_CB cells
+// (GSF_CB independent accumulation chains per thread, each summed over the nodes in the Fortran order with separate multiply
+// and add roundings).  (Rejected: staging the table through shared memory in node chunks with one thread per moment index --
+// 0.223 ms against 0.126 ms for k_gsf on 2196 cells: two barriers per chunk and 16 shared loads per 24 FP64 instructions.)
+#ifndef GSF_CB
+#define GSF_CB 2   // 2196 optics_SU cells: k_gsf 0.127 ms, CB = 2: 0.101, 3: 0.105, 4: 0.196 (fewer, fatter CTAs: wave quantisation)
+#endif
+
+__global__ void __launch_bounds__(256) k_gsf_multi(int nrow, int nang, int ng, int ncell, const double* __restrict__ F,
+                                                   const GsfNode* __restrict__ nodes, const double* __restrict__ G,
+                                                   double* __restrict__ coef, double* __restrict__ cnorm, int quantize10,
+                                                   double* __restrict__ raw) {
+  extern __shared__ double sm[];
+  double* f = sm;                              // [6][nang]            one cell at a time
+  double* ff = f + 6 * nang;                   // [CB][6][ng]          FF11, FP, FM, FF44, FF12, FF34 at the nodes
+  double* res = ff + GSF_CB * 6 * ng;          // [CB][6][ng]
+  const int cell0 = blockIdx.x * GSF_CB;
+  const int ncb = min(GSF_CB, ncell - cell0);
+  // ---- interpolation to the Gauss nodes, cell by cell (LINTERPOL, one_calc :159-166; weights :316-321)
+  for (int c = 0; c < GSF_CB; ++c) {
+    if (c >= ncb) {
+      for (int k = threadIdx.x; k < 6 * ng; k += blockDim.x) ff[(size_t)c * 6 * ng + k] = 0.0;
+      continue;
+    }
+    const double* Fc = F + (size_t)(cell0 + c) * nrow * nang;
+    __syncthreads();
+    for (int k = threadIdx.x; k < 6 * nang; k += blockDim.x) {
+      int row = k / nang;
+      if (nrow == 4) row = (row == 0 || row == 1) ? 0 : (row == 2 || row == 3) ? 2 : (row == 4 ? 1 : 3);
+      f[k] = Fc[row * nang + k % nang];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < ng; i += blockDim.x) {
+      const GsfNode nd = nodes[i];
+      double v[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const double y0 = f[k * nang + nd.i0], y1 = f[k * nang + nd.i1];
+        v[k] = __dadd_rn(__dmul_rn(__ddiv_rn(__dsub_rn(y1, y0), nd.dx), nd.dxinv_num), y0);
+        v[k] = __dmul_rn(v[k], nd.w);
+      }
+      double* o = ff + (size_t)c * 6 * ng + i;
+      o[0 * ng] = v[0];
+      o[1 * ng] = __dadd_rn(v[1], v[2]);
+      o[2 * ng] = __dsub_rn(v[1], v[2]);
+      o[3 * ng] = v[3];
+      o[4 * ng] = v[4];
+      o[5 * ng] = v[5];
+    }
+  }
+  __syncthreads();
+  // ---- accumulation over the nodes in the Fortran order (DO 300 I / DO 260 L1), one thread per (series, l), GSF_CB cells
+  for (int o = threadIdx.x; o < 6 * ng; o += blockDim.x) {
+    const int s6 = o / ng, l = o % ng;
+    // series: 0 AL1 (FF11,P1) 1 AL2acc (FP,P2) 2 AL3acc (FM,P3) 3 AL4 (FF44,P1) 4 BET1 (FF12,P4) 5 BET2 (FF34,P4)
+    const int gsel = (s6 == 0 || s6 == 3) ? 0 : (s6 == 1 ? 1 : (s6 == 2 ? 2 : 3));
+    const double* g = G + (size_t)gsel * ng * ng + l;
+    const double* w = ff + s6 * ng;
+    double acc[GSF_CB];
+#pragma unroll
+    for (int c = 0; c < GSF_CB; ++c) acc[c] = 0.0;
+#pragma unroll 8
+    for (int i = 0; i < ng; ++i) {
+      const double gv = g[(size_t)i * ng];
+#pragma unroll
+      for (int c = 0; c < GSF_CB; ++c) acc[c] = __dadd_rn(acc[c], __dmul_rn(w[(size_t)c * 6 * ng + i], gv));
+    }
+#pragma unroll
+    for (int c = 0; c < GSF_CB; ++c) res[(size_t)c * 6 * ng + o] = acc[c];
+  }
+  __syncthreads();
+  // ---- DO 350: scaling by (l + 1/2), AL2/AL3 recombination, CNORM = 1/AL1(1)
+  for (int e = threadIdx.x; e < ncb * ng; e += blockDim.x) {
+    const int c = e / ng, lo = e % ng;
+    const double* r = res + (size_t)c * 6 * ng;
+    const double cn = 1.0 / (r[0] * 0.5);
+    const double CL = (double)lo + 0.5;
+    const double al1 = r[0 * ng + lo] * CL;
+    const double a2 = r[1 * ng + lo] * CL * 0.5;
+    const double a3 = r[2 * ng + lo] * CL * 0.5;
+    double o[6] = {al1, a2 + a3, a2 - a3, r[3 * ng + lo] * CL, r[4 * ng + lo] * CL, r[5 * ng + lo] * CL};
+    const size_t cell = (size_t)(cell0 + c);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      double v = o[k] * cn;
+      if (quantize10) v = rint(v * 1e10) / 1e10;
+      coef[(cell * 6 + k) * ng + lo] = v;
+      if (raw) raw[(cell * 6 + k) * ng + lo] = o[k];
+    }
+    if (lo == 0 && cnorm) cnorm[cell] = cn;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ diagnostics
@@ -383,10 +479,18 @@ int gsf_core(gm_handle_t h, int ncell, int nang, const double* h_ang_deg, const 
     if ((rc0 = h->gsf_raw.ensure(sizeof(double) * (size_t)ncell * 6 * ng))) return rc0;
     d_raw = h->gsf_raw.as<double>();
   }
-  const size_t smem = sizeof(double) * (6 * (size_t)nang + 12 * (size_t)ng);
-  GM_CUDA_TRY(cudaFuncSetAttribute(k_gsf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_gsf<<<ncell, 256, smem, st>>>(nrow, nang, ng, d_F, h->gsf_nodes.as<GsfNode>(), h->gsf_table.as<double>(), d_coef, d_cnorm, quantize10,
-                                  d_raw);
+  const bool force_simple = getenv("GEOSMIE_GSF_SIMPLE") != nullptr;   // cross-check of the two kernels (tests)
+  const size_t smem_multi = sizeof(double) * (6 * (size_t)nang + (size_t)(2 * GSF_CB * 6) * ng);
+  if (ncell >= 2 * GSF_CB && smem_multi <= 200 * 1024 && !force_simple) {
+    GM_CUDA_TRY(cudaFuncSetAttribute(k_gsf_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_multi));
+    k_gsf_multi<<<(ncell + GSF_CB - 1) / GSF_CB, 256, smem_multi, st>>>(nrow, nang, ng, ncell, d_F, h->gsf_nodes.as<GsfNode>(),
+                                                                      h->gsf_table.as<double>(), d_coef, d_cnorm, quantize10, d_raw);
+  } else {
+    const size_t smem = sizeof(double) * (6 * (size_t)nang + 12 * (size_t)ng);
+    GM_CUDA_TRY(cudaFuncSetAttribute(k_gsf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_gsf<<<ncell, 256, smem, st>>>(nrow, nang, ng, d_F, h->gsf_nodes.as<GsfNode>(), h->gsf_table.as<double>(), d_coef, d_cnorm, quantize10,
+                                    d_raw);
+  }
   GM_LAUNCH_CHECK(h);
   if (diag) {
     const size_t smem2 = sizeof(double) * (6 * (size_t)ng + (size_t)nang);
