@@ -12,7 +12,8 @@
 #include "gm_gram.cuh"
 
 #ifndef GM_HIO_MIN_BATCHES
-#define GM_HIO_MIN_BATCHES 3     // host-buffer calls: batches whose H2D / D2H copies are pipelined against the kernels (optics_SU e2e: 2 -> 3.92, 3 -> 3.72, 4 -> 3.87, 6 -> 4.1 ms)
+#define GM_HIO_MIN_BATCHES 3     // host-buffer calls: batches whose H2D / D2H copies are pipelined against the kernels (optics_SU e2e, equal batches: 2 -> 3.92, 3 -> 3.72, 4 -> 3.87, 6 -> 4.1 ms)
+#define GM_HIO_SPLIT {42, 42, 16}   // per cent of the tasks in each batch (optics_SU e2e: 34/33/33 3.74 ms, 40/36/24 3.67, 50/35/15 3.64, 42/42/16 3.60)
 #endif
 #ifndef GM_GRAM_INTERLEAVE
 #define GM_GRAM_INTERLEAVE 1     // k_gram launch order: HBM-bound (class 0/1) work items interleaved with the pipe-bound ones
@@ -551,7 +552,43 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
     if ((rc = t->c_ab.ensure((size_t)tb * t->c_nab * sizeof(double4))) || (rc = t->c_scratch.ensure((size_t)tb * t->c_nscr * 8 * sizeof(double))))
       return rc;
   }
-  if (hio && ntask >= 256) tb = std::min(tb, (ntask + GM_HIO_MIN_BATCHES - 1) / GM_HIO_MIN_BATCHES);   // several batches so that copies overlap compute
+  // Batch boundaries.  Device-pointer calls: as few batches as the scratch budget allows.  Host-buffer calls: at least
+  // GM_HIO_MIN_BATCHES batches so that the copies overlap the kernels, of DECREASING size -- the download of the last batch is the
+  // one transfer nothing can hide, so that batch is the smallest (GM_HIO_SPLIT, per cent of the tasks).
+  std::vector<int> bstart(1, 0);
+  if (hio && ntask >= 256) {
+    static const int split[GM_HIO_MIN_BATCHES] = GM_HIO_SPLIT;
+    const char* env = getenv("GEOSMIE_HIO_SPLIT");   // experiments: "45,35,20"
+    int pct[GM_HIO_MIN_BATCHES], sum = 0;
+    for (int b = 0; b < GM_HIO_MIN_BATCHES; ++b) pct[b] = split[b];
+    if (env) {
+      int k = 0;
+      for (const char* p = env; *p && k < GM_HIO_MIN_BATCHES; ++k) {
+        pct[k] = atoi(p);
+        while (*p && *p != ',') ++p;
+        if (*p == ',') ++p;
+      }
+    }
+    for (int b = 0; b < GM_HIO_MIN_BATCHES; ++b) sum += std::max(pct[b], 1);
+    int acc = 0;
+    for (int b = 0; b + 1 < GM_HIO_MIN_BATCHES; ++b) {
+      acc += std::max(pct[b], 1);
+      const int e = (int)((long long)ntask * acc / sum);
+      if (e > bstart.back() && e < ntask) bstart.push_back(e);
+    }
+    bstart.push_back(ntask);
+    // a part larger than the scratch budget is cut further
+    std::vector<int> cut(1, 0);
+    for (size_t b = 0; b + 1 < bstart.size(); ++b)
+      for (int t0 = bstart[b]; t0 < bstart[b + 1]; t0 += tb) cut.push_back(std::min(bstart[b + 1], t0 + tb));
+    bstart.swap(cut);
+    int largest = 0;
+    for (size_t b = 0; b + 1 < bstart.size(); ++b) largest = std::max(largest, bstart[b + 1] - bstart[b]);
+    tb = largest;
+  } else {
+    for (int t0 = tb; t0 < ntask; t0 += tb) bstart.push_back(t0);
+    bstart.push_back(ntask);
+  }
   const bool use_gram = !per_particle && !(flags & GM_F_NO_GRAM) && !G.glist.empty();
   const int ndirect = use_gram ? G.ndirect : G.ngroup;
   // chunks of the per-angle contraction: enough CTAs to fill the machine ~8x over, cost-balanced by the k4 steps of the
@@ -578,7 +615,7 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
     nchunk = (int)cstart.size() - 1;
   }
   const int nchunk_total = nchunk + (use_gram ? 1 : 0);
-  const int nbatch = (ntask + tb - 1) / tb;
+  const int nbatch = (int)bstart.size() - 1;
   // Gram plan(s): descriptors (class, group range, partial slot) and CTA work items (descriptor, task range) per batch size
   struct GramPlan {
     int nt = 0, desc0 = 0, ndesc = 0, item0 = 0, nitem = 0;
@@ -589,8 +626,10 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
   std::vector<GramItem> all_items;
   if (use_gram) {
     for (int b = 0; b < nbatch; ++b) {
-      const int nt = std::min(tb, ntask - b * tb);
-      if (!plans.empty() && plans.back().nt == nt) continue;
+      const int nt = bstart[b + 1] - bstart[b];
+      bool have = false;
+      for (auto& q : plans) have |= q.nt == nt;
+      if (have) continue;
       GramPlan P;
       P.nt = nt;
       P.desc0 = (int)all_desc.size();
@@ -703,7 +742,7 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
     GM_CUDA_TRY(cudaStreamWaitEvent(t->h2d_stream, t->io_events[2 * nbatch], 0));
     GM_CUDA_TRY(cudaStreamWaitEvent(t->d2h_stream, t->io_events[2 * nbatch], 0));
     for (int b = 0; b < nbatch; ++b) {
-      const int t0 = b * tb, nt = std::min(tb, ntask - t0);
+      const int t0 = bstart[b], nt = bstart[b + 1] - t0;
       if (hio->w_phase)
         GM_CUDA_TRY(cudaMemcpyAsync(const_cast<double*>(d_wphase) + (size_t)t0 * G.nx, hio->w_phase + (size_t)t0 * G.nx,
                                     sizeof(double) * (size_t)nt * G.nx, cudaMemcpyHostToDevice, t->h2d_stream));
@@ -714,9 +753,8 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
     }
   }
 
-  for (int t0 = 0; t0 < ntask; t0 += tb) {
-    const int nt = std::min(tb, ntask - t0);
-    const int bi = t0 / tb;
+  for (int bi = 0; bi < nbatch; ++bi) {
+    const int t0 = bstart[bi], nt = bstart[bi + 1] - t0;
     if (hio) GM_CUDA_TRY(cudaStreamWaitEvent(st, t->io_events[bi], 0));
     CoeffArgs A;
     memset(&A, 0, sizeof(A));
