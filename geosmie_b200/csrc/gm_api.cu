@@ -82,6 +82,7 @@ extern "C" int gm_destroy(gm_handle_t h) {
   h->gsf_nodes.release();
   h->gsf_table.release();
   h->gsf_alt.release();
+  h->ntab.release();
   h->gsf_raw.release();
   if (h->peer_stream) cudaStreamDestroy(h->peer_stream);
   if (h->peer_ev_compute) cudaEventDestroy(h->peer_ev_compute);
@@ -112,6 +113,25 @@ extern "C" int64_t gm_launch_count(gm_handle_t h) { return h ? h->launches : 0; 
     (h)->launches++;                     \
     GM_CUDA_TRY(cudaGetLastError());     \
   } while (0)
+
+// order-dependent factors of the efficiency sums (mie_props.py:58-64) for every order up to nmaxmax, evaluated once on the host
+static int ensure_ntab(gm_handle_s* h, int nmaxmax) {
+  if (nmaxmax + 2 <= h->ntab_n) return GM_OK;
+  int n = 4096;
+  while (n < nmaxmax + 2) n *= 2;
+  std::vector<double> v((size_t)2 * n, 0.0);
+  for (int k = 1; k < n; ++k) {
+    const double dn = (double)k;
+    v[2 * (size_t)k] = (2.0 * dn + 1.0) / (dn * (dn + 1.0));
+    v[2 * (size_t)k + 1] = dn * (dn + 2.0) / (dn + 1.0);
+  }
+  GM_CUDA_TRY(cudaStreamSynchronize(h->stream));   // kernels still reading the old table
+  int rc = h->ntab.ensure(sizeof(double) * v.size());
+  if (rc) return rc;
+  GM_CUDA_TRY(cudaMemcpy(h->ntab.p, v.data(), sizeof(double) * v.size(), cudaMemcpyHostToDevice));
+  h->ntab_n = n;
+  return GM_OK;
+}
 
 // ------------------------------------------------------------------------------------------------ grouping
 // Host description of how a particle list is cut into groups of 32 (one warp of k_coeff, one N-extent of k_contract).
@@ -304,6 +324,8 @@ extern "C" int gm_mie_eval(gm_handle_t h, int n, const double* x, const double* 
     A.ngroup = G.ngroup;
     A.x = W[0].as<double>();
     A.nmax = W[1].as<int>();
+    if ((rc = ensure_ntab(h, G.nmaxmax))) return rc;
+    A.ntab = h->ntab.as<double2>();
     A.psi = W[3].as<double>();
     A.chi = W[4].as<double>();
     A.gboff = W[2].as<long long>();
@@ -725,6 +747,7 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
   const int smem = GM_CONTRACT_SMEM;
   for (int c = 0; c < nchunk; ++c)
     GM_REQUIRE(cstart[c + 1] - cstart[c] <= GM_MAX_CHUNK_GROUPS, "chunk has more particle groups than the smem metadata holds");
+  if ((rc = ensure_ntab(h, G.nmaxmax))) return rc;
   const int64_t launches0 = h->launches;
   t->evused = 0;
   if (hio) {
@@ -762,6 +785,7 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
     A.ngroup = G.ngroup;
     A.x = t->D.x.as<double>();
     A.nmax = t->D.nmax.as<int>();
+    A.ntab = h->ntab.as<double2>();
     A.psi = t->D.psi.as<double>();
     A.chi = t->D.chi.as<double>();
     A.gboff = t->D.gboff.as<long long>();

@@ -72,6 +72,9 @@ struct gm_handle_s {
   DevBuf gsf_nodes, gsf_table, gsf_alt, gsf_raw;
   std::vector<double> gsf_key;
   bool gsf_alt_valid = false;
+  // per-order constants of k_coeff: [n] = ((2n+1)/(n(n+1)), n(n+2)/(n+1)) (mie_props.py:58-64), grown on demand
+  DevBuf ntab;
+  int ntab_n = 0;
   // multi-GPU exchange (gm_peer.cu): copy-engine transfers run on their own stream, ordered against `stream` by events
   cudaStream_t peer_stream = nullptr;
   cudaEvent_t peer_ev_compute = nullptr, peer_ev_done = nullptr;

@@ -159,6 +159,8 @@ struct CoeffArgs {
   long long ab_stride;
   double* q;               // [ntask][nx][6] (nullable)
   unsigned long long* stats;  // [0] evals [1] sum nmax [2] sum nmx [3] padded k4 steps
+  const double2* ntab;        // [n] = ((2n+1)/(n(n+1)), n(n+2)/(n+1)): the order-dependent factors of mie_props_raw, read with a
+                              // warp-uniform index instead of two reciprocals per order
 };
 
 // MODE 0: DMMA group layout (c+ = (a+b) f_n sqrt(w), c- = (a-b) f_n sqrt(w)); MODE 1: natural a_n, b_n;
@@ -292,15 +294,15 @@ __global__ void __launch_bounds__(128, GM_COEFF_MINB) k_coeff(CoeffArgs A) {
         chi_n = chi_m;
       }
       // efficiencies, mie_props.py:41-65
-      const double cn = 2.0 * dn + 1.0;
-      const double rn1 = fast_rcp(dn + 1.0);
-      const double c2n = cn * rn1 * fast_rcp(dn);             // (2n+1)/(n(n+1))
+      const double cn = f2;                                   // 2n + 1
+      const double2 nt = __ldg(A.ntab + n);
+      const double c2n = nt.x;                                // (2n+1)/(n(n+1))
       sext += cn * (an.x + bn.x);
       ssca += cn * (an.x * an.x + an.y * an.y + bn.x * bn.x + bn.y * bn.y);
       const double sg = (n & 1) ? -cn : cn;
       qbr += sg * (an.x - bn.x);
       qbi += sg * (an.y - bn.y);
-      sasy += dn * (dn + 2.0) * rn1 * (an.x * a_next.x + an.y * a_next.y + bn.x * b_next.x + bn.y * b_next.y) +
+      sasy += nt.y * (an.x * a_next.x + an.y * a_next.y + bn.x * b_next.x + bn.y * b_next.y) +
               c2n * (an.x * bn.x + an.y * bn.y);
       a_next = an;
       b_next = bn;
