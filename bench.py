@@ -240,7 +240,9 @@ def main():
         from geosmie_b200 import dist
         comm = dist.Comm(rank, world, device=local)
         gather_mode = os.environ.get("GEOSMIE_GATHER", "peer")
-        if gather_mode in ("peer", "store"):
+        if gather_mode == "off":             # diagnostic: independent replicas, nothing leaves the GPU
+            pass
+        elif gather_mode in ("peer", "store"):
             pg = comm.peer_gather((nscal + nph + nco) * 8, nslot=2, handle=h)
             if pg is None:
                 gather_mode = "nccl"
@@ -256,6 +258,8 @@ def main():
         i = step_no[0] & 1
         step_no[0] += 1
         sd, pd, cd = outs_d[i % len(outs_d)]
+        if gather_mode == "off":
+            return
         if gather_mode in ("peer", "store"):
             if gather_mode == "store" and src is None:
                 return                          # the kernels of this step already stored into slot i (see step_device)
@@ -326,6 +330,8 @@ def main():
             if pg is not None:
                 h.peer_mark(2)
 
+    per_rank_ms = []            # [timed region][rank] ms per step (multi-GPU diagnostics)
+
     def barrier():
         if world > 1:
             td.barrier()
@@ -344,20 +350,25 @@ def main():
         ms = e0.elapsed_time(e1)
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            td.all_reduce(t, op=td.ReduceOp.MAX)
-            ms = float(t.item())
+            every = [torch.zeros_like(t) for _ in range(world)]
+            td.all_gather(every, t)
+            per_rank_ms.append([float(x.item()) / steps for x in every])
+            ms = max(float(x.item()) for x in every)              # the slowest rank defines the step
         return ms / steps
 
     for _ in range(max(args.warmup, 3)):
         step_device()
     launches0 = h.launch_count()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
+    sampler = ClockSampler(local)          # every rank samples its own GPU; rank 0 reports its own and the slowest
+    sampler.start()
+    time.sleep(0.3)
     ms_dev = timed(step_device, args.steps)
     launches = (h.launch_count() - launches0) // args.steps
     kms = table.last_kernel_ms()            # CUDA events around the launches of the LAST timed step
+    per_rank_kernel_ms = None
+    if world > 1:
+        per_rank_kernel_ms = [None] * world
+        td.all_gather_object(per_rank_kernel_ms, {k: round(kms[k], 4) for k in ("k_coeff", "k_gram", "k_gram_sum_eval", "k_finalize")})
     stats = table.last_stats()
     table.set_mirror(None, None)
     table.set_gsf(ang, 129, False, coef_hn, None)
@@ -369,7 +380,16 @@ def main():
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
     table.set_gsf(None)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop()
+    if world > 1:
+        allc = [None] * world
+        td.all_gather_object(allc, clocks)
+        clocks = dict(allc[0])
+        clocks["per_rank_sm_mhz"] = [c.get("sm_mhz") for c in allc]
+        clocks["reasons"] = sorted(set(r for c in allc for r in c.get("reasons", [])))
+        known = [c["sm_mhz"] for c in allc if c.get("sm_mhz")]
+        if known:
+            clocks["sm_mhz"] = min(known)              # the slowest GPU of the job
 
     total_evals = float(ncell) * nx * world
     value = total_evals / (ms_dev * 1e-3)
@@ -410,7 +430,7 @@ def main():
                    "parallelism": "cells sharded, %d rank(s), gather to rank 0: %s (overlapped with the next step, complete inside the timed region)"
                                   % (world, {"peer": "copy-engine puts into rank 0's IPC-mapped buffer over NVLink (gm_peer_put)",
                                              "store": "P2P stores of k_finalize / k_gsf into rank 0's IPC-mapped buffer",
-                                             "nccl": "NCCL gather", "none": "none (1 rank)"}[gather_mode])},
+                                             "nccl": "NCCL gather", "none": "none (1 rank)", "off": "SWITCHED OFF (diagnostic run)"}[gather_mode])},
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(mz_psd.nbytes * 2 + psd_par.nbytes + psd_frac.nbytes),
                 "api": "gm_table_run_psd with the fused GSF stage (host buffers: per-cell m and PSD parameters in, reduced sums and GSF moments out)",
@@ -446,6 +466,9 @@ def main():
         ms_el = timed(step_elide, args.steps) if world == 1 else None
         line["elided"] = {"ms_per_step": ms_el, "grid_evals_per_sec": total_evals / world / (ms_el * 1e-3) if ms_el else None,
                           "evaluated": table.last_stats()["evals"]}
+    if world > 1:
+        line["per_rank_ms_per_step"] = {"device": per_rank_ms[0], "e2e": per_rank_ms[1] if len(per_rank_ms) > 1 else None}
+        line["per_rank_kernel_ms"] = per_rank_kernel_ms
     if rank == 0:
         print(json.dumps(line))
     table.close()

@@ -68,6 +68,15 @@ extern "C" int gm_init(int device, gm_handle_t* out) {
   GM_CUDA_TRY(cudaFuncSetAttribute(k_gram_eval<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_GRAM_EVAL_SMEM_MAX));
   GM_CUDA_TRY(cudaFuncSetAttribute(k_gram_eval<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_GRAM_EVAL_SMEM_MAX));
   GM_CUDA_TRY(cudaFuncSetAttribute(k_gram_eval<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_GRAM_EVAL_SMEM_MAX));
+  // Experiment switch (GEOSMIE_COEFF_CARVEOUT=maxl1): ask for the largest L1 for k_coeff, which uses no shared memory.  Tried
+  // against the rank-dependent slow mode of k_coeff in multi-GPU jobs (1.6-1.86 ms instead of 1.03 ms):
+  // no effect (4 GPUs, same box: 3.77 ms/step without, 3.75 ms with), so the driver's default stays.
+  const char* cv = getenv("GEOSMIE_COEFF_CARVEOUT");
+  if (cv && !strcmp(cv, "maxl1")) {
+    GM_CUDA_TRY(cudaFuncSetAttribute(k_coeff<0>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxL1));
+    GM_CUDA_TRY(cudaFuncSetAttribute(k_coeff<1>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxL1));
+    GM_CUDA_TRY(cudaFuncSetAttribute(k_coeff<2>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxL1));
+  }
   *out = h;
   return GM_OK;
 }
