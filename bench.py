@@ -41,8 +41,8 @@ NANG = 371
 FP64_PEAK_TFLOPS = 37.1   # measured on this pool's B200 with tools/fp64_peak.cu (DMMA m8n8k4), profiles/r01_fp64_peak.json
 FP64_DFMA_PEAK_TFLOPS = 33.5   # same tool, plain DFMA (the pipe k_coeff runs on)
 # dram__bytes_read.sum + dram__bytes_write.sum of k_gram per SU cell, from the `ncu --set full` capture
-# profiles/r01h_gram_su_549cells.ncu-rep (726.42 MB + 164.86 MB over 549 dense cells)
-GRAM_DRAM_BYTES_PER_CELL = (726.423808e6 + 164.859136e6) / 549
+# profiles/r01k_gram_su_732cells.ncu-rep (968.82 MB + 196.93 MB over 732 dense cells)
+GRAM_DRAM_BYTES_PER_CELL = (968.823552e6 + 196.926976e6) / 732
 
 
 def build_su_plan():
@@ -117,6 +117,44 @@ class ClockSampler(threading.Thread):
         load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
         return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
                 "samples": len(sm)}
+
+
+class FastPowerSampler(threading.Thread):
+    """Best-effort second sampler (50 ms period): lowest SM clock, highest power draw and the HW power-brake flag during the
+    timed region.  Added to find out why k_coeff runs 1.6-1.9 ms instead of 1.03 ms on some ranks of a multi-GPU job although
+    the 100 ms sampler sees 1965 MHz everywhere.  A driver that does not know one of the fields makes
+    nvidia-smi print nothing; the result is then simply empty."""
+
+    Q = "clocks.sm,power.draw,clocks_event_reasons.hw_power_brake_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, pw, brake, cap = [], [], False, False
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                pw.append(float(r[1]))
+                brake |= r[2].lower().startswith("active")
+                cap |= r[3].lower().startswith("active")
+            except Exception:
+                continue
+        if not sm:
+            return {}
+        return {"sm_mhz_min": min(sm), "power_w_max": max(pw), "hw_power_brake": brake, "sw_power_cap": cap, "fast_samples": len(sm)}
 
 
 def cpu_baseline(plan, seconds=12.0, threads=None):
@@ -361,6 +399,8 @@ def main():
     launches0 = h.launch_count()
     sampler = ClockSampler(local)          # every rank samples its own GPU; rank 0 reports its own and the slowest
     sampler.start()
+    fast = FastPowerSampler(local)
+    fast.start()
     time.sleep(0.3)
     ms_dev = timed(step_device, args.steps)
     launches = (h.launch_count() - launches0) // args.steps
@@ -381,11 +421,16 @@ def main():
     ms_e2e = timed(step_e2e, args.steps)
     table.set_gsf(None)
     clocks = sampler.stop()
+    clocks.update(fast.stop())
     if world > 1:
         allc = [None] * world
         td.all_gather_object(allc, clocks)
         clocks = dict(allc[0])
         clocks["per_rank_sm_mhz"] = [c.get("sm_mhz") for c in allc]
+        clocks["per_rank_sm_mhz_min"] = [c.get("sm_mhz_min") for c in allc]
+        clocks["per_rank_power_w_max"] = [c.get("power_w_max") for c in allc]
+        clocks["hw_power_brake"] = any(c.get("hw_power_brake") for c in allc)
+        clocks["sw_power_cap"] = any(c.get("sw_power_cap") for c in allc)
         clocks["reasons"] = sorted(set(r for c in allc for r in c.get("reasons", [])))
         known = [c["sm_mhz"] for c in allc if c.get("sm_mhz")]
         if known:
