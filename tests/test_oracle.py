@@ -183,3 +183,48 @@ def test_fortran_edit_descriptors():
     assert back.shape == (7, 2) and np.max(np.abs(back[1:] - coef)) <= 0.5e-10
     m = se.format_expan_matr(np.array([0.0, 90.0, 180.0]), np.ones((6, 3)))
     assert m.splitlines()[2] == "180.00" + " " + "    0.10000E+01" * 4 + "    1.00000" * 2
+
+
+def test_spher_expan_text_protocol_with_oracle_backend(tmp_path):
+    """The drop-in for ./spher_expan.x (file grouping, formats, what the reference's consumer reads back) with the oracle
+    standing in for the GPU handle: input text -> <file>.expan_coeff / <file>.expan_matr (convertncdf.py:185-189, :381-394)."""
+    from geosmie_b200.gsf import spher_expan as se
+
+    class OracleHandle(object):
+        calls = 0
+
+        def gsf_diagnose(self, ang, F, ng=129, quantize10=False):
+            OracleHandle.calls += 1
+            co, cn, fo, er = [], [], [], []
+            for k in range(F.shape[0]):
+                c, n = go.expand(ang, F[k], ng)
+                f, e = go.one_calc(ang, F[k], ng)
+                co.append(c); cn.append(n); fo.append(f); er.append(e)
+            return np.array(co), np.array(cn), np.array(fo), np.array(er)
+
+    ang = table_angles()
+    uni = np.linspace(0., 180., 181)
+    files, mats = [], []
+    for i, a in enumerate((ang, uni, ang)):            # two angle grids: files 0 and 2 are expanded together
+        F = rayleigh(a) * (1.0 + 0.1 * i)
+        allvals = np.zeros((7, a.size))
+        allvals[0], allvals[1:] = a, F
+        fn = str(tmp_path / ("x.tempfile%d.txt" % i))
+        np.savetxt(fn, allvals.T)
+        files.append(fn)
+        mats.append((a, F))
+    out = se.expand_files(files, handle=OracleHandle())
+    assert OracleHandle.calls == 2 and set(out) == set(files)
+    for fn, (a, F) in zip(files, mats):
+        newdata = np.loadtxt(fn + ".expan_coeff", skiprows=1, unpack=True)
+        co, cn = go.expand(a, F, quantize10=True)
+        assert newdata.shape == (7, 129) and np.max(np.abs(newdata[1:] - co)) <= 1e-10 + 1e-15
+        assert abs(newdata[1, 0] - 1.0) < 1e-9                      # normalised by AL1(0)
+        matr = np.loadtxt(fn + ".expan_matr")
+        assert matr.shape == (a.size, 7) and np.max(np.abs(matr[:, 0] - a)) <= 0.005
+        assert np.max(np.abs(matr[:, 1] - F[0])) < 2e-4 * 1.2        # re-synthesis reproduces F11 to the interpolation limit
+        assert out[fn] < 2.5e-4
+    bad = str(tmp_path / "bad.txt")
+    np.savetxt(bad, np.zeros((5, 3)))
+    with pytest.raises(ValueError):
+        se.expand_files([bad], handle=OracleHandle())
