@@ -369,6 +369,7 @@ def main():
                 h.peer_mark(2)
 
     per_rank_ms = []            # [timed region][rank] ms per step (multi-GPU diagnostics)
+    stagger_ms = float(os.environ.get("GEOSMIE_BENCH_STAGGER_MS", "0") or 0.0)
 
     def barrier():
         if world > 1:
@@ -379,6 +380,10 @@ def main():
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
+        if stagger_ms > 0.0 and world > 1:
+            # experiment (off by default, GEOSMIE_BENCH_STAGGER_MS=<step ms>): rank r starts r/world of a step late, INSIDE the
+            # timed region, so that the ranks do not run the same kernel at the same instant
+            time.sleep(1e-3 * stagger_ms * rank / world)
         for _ in range(steps):
             fn()
         if world > 1:
