@@ -345,6 +345,7 @@ extern "C" int gm_mie_eval(gm_handle_t h, int n, const double* x, const double* 
     A.ab = W[8].as<double4>();
     A.q = W[9].as<double>();
     dim3 grid((G.ngroup + 3) / 4, 1);
+    A.ntask = 1;
     k_coeff<1><<<grid, 128, 0, st>>>(A);
     GM_LAUNCH_CHECK(h);
   }
@@ -804,6 +805,7 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
     A.wphase = d_wphase ? d_wphase + (size_t)t0 * G.nx : nullptr;
     A.wscal = d_wscal ? d_wscal + (size_t)t0 * nmode * G.nx : nullptr;
     A.nmode = nmode;
+    A.ntask = nt;
     A.dense = (flags & GM_F_ELIDE_ZERO_WEIGHT) ? 0 : 1;
     A.scale_sqrtw = per_particle ? 0 : 1;
     A.grow = t->D.grow.as<int>();
@@ -832,9 +834,9 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
       A.aboff = t->c_aboff.as<long long>();
       A.ab = t->c_ab.as<double4>();
       A.ab_stride = t->c_nab;
-      k_coeff<2><<<dim3((G.ngroup + 3) / 4, nt), 128, 0, st>>>(A);
+      k_coeff<2><<<dim3((G.ngroup + 3) / 4, (nt + GM_COEFF_TPC - 1) / GM_COEFF_TPC), 128, 0, st>>>(A);
     } else {
-      k_coeff<0><<<dim3((G.ngroup + 3) / 4, nt), 128, 0, st>>>(A);
+      k_coeff<0><<<dim3((G.ngroup + 3) / 4, (nt + GM_COEFF_TPC - 1) / GM_COEFF_TPC), 128, 0, st>>>(A);
     }
     GM_LAUNCH_CHECK(h);
     if ((rc = ev_mark(t, 0))) return rc;

@@ -159,6 +159,7 @@ struct CoeffArgs {
   long long ab_stride;
   double* q;               // [ntask][nx][6] (nullable)
   unsigned long long* stats;  // [0] evals [1] sum nmax [2] sum nmx [3] padded k4 steps
+  int ntask;                  // tasks of this launch (bound of the task loop when GM_COEFF_TPC > 1)
   const double2* ntab;        // [n] = ((2n+1)/(n(n+1)), n(n+2)/(n+1)): the order-dependent factors of mie_props_raw, read with a
                               // warp-uniform index instead of two reciprocals per order
 };
@@ -168,16 +169,31 @@ struct CoeffArgs {
 #ifndef GM_COEFF_MINB
 #define GM_COEFF_MINB 4   // 16 warps per SM without spills; at 5 (96 registers) the 16-value reduction spills 12 B and the kernel ran 1.9 ms instead of 1.05 ms on some boxes
 #endif
+// GM_COEFF_TPC (experiment, default 1 = one task per CTA, unchanged code): tasks a CTA works through for its four particle
+// groups.  With 1 the optics_SU step launches 76,860 CTAs of ~8 us each for this kernel; > 1 makes them proportionally fewer and
+// longer and lets the Riccati-Bessel rows, x and nmax of the group stay in L1 / registers across the tasks.  Prepared for the
+// rank-dependent slow mode of this kernel in multi-GPU jobs; not yet measured.
+#ifndef GM_COEFF_TPC
+#define GM_COEFF_TPC 1
+#endif
+#if GM_COEFF_TPC == 1
+#define GM_COEFF_TASK_LOOP const int task = blockIdx.y;
+#define GM_COEFF_NEXT_TASK return
+#else
+#define GM_COEFF_TASK_LOOP \
+  for (int task = blockIdx.y * GM_COEFF_TPC; task < min(A.ntask, (int)(blockIdx.y + 1) * GM_COEFF_TPC); ++task)
+#define GM_COEFF_NEXT_TASK continue
+#endif
 template <int MODE>
 __global__ void __launch_bounds__(128, GM_COEFF_MINB) k_coeff(CoeffArgs A) {
   const int g = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (g >= A.ngroup) return;
   const int lane = threadIdx.x & 31;
   const int i = g * 32 + lane;
-  const int task = blockIdx.y;
   const bool valid = i < A.nx;
   const double xi = valid ? A.x[i] : 1.0;
   const int nm = valid ? A.nmax[i] : 0;
+  GM_COEFF_TASK_LOOP {
   const int mi = A.mat_per_particle ? (valid ? i : 0) : task;
   const double2 mzv = A.mz[mi];
   const double2 mrv = A.mrel[mi];
@@ -203,7 +219,7 @@ __global__ void __launch_bounds__(128, GM_COEFF_MINB) k_coeff(CoeffArgs A) {
     if (!gactive) {
       for (int k = lane; k < A.nmode * GM_NSCAL; k += 32)
         A.scal_part[(((size_t)task * A.nmode + k / GM_NSCAL) * A.ngroup + g) * GM_NSCAL + k % GM_NSCAL] = 0.0;
-      return;
+      GM_COEFF_NEXT_TASK;
     }
   }
   const size_t bbase = (size_t)A.gboff[g] + lane;
@@ -381,6 +397,7 @@ __global__ void __launch_bounds__(128, GM_COEFF_MINB) k_coeff(CoeffArgs A) {
       if (!(lane & 1) && s < GM_NSCAL) o[s] = r;
     }
   }
+  }   // GM_COEFF_TASK_LOOP
 }
 
 // ================================================================================================ k_contract
