@@ -456,6 +456,21 @@ class BinPlan(object):
         want = None if cells is None else set(cells)
         if device_psd and want:
             want |= {(li, 0) for (li, _) in want}      # reff_mass0 comes from the RH-index-0 cell of the same wavelength
+        with pp.growth_memo():
+            self._scan_cells(params, radind, lambarr, rh_used, part_m, water_m, want, trivial, device_psd, mr_l, w_l, par_l, meta)
+        ncell, nmode = len(self.cells), len(self.fracs)
+        self.m = np.array(mr_l, dtype=np.complex128).reshape(ncell, self.nri)
+        self.w = None if device_psd else np.array(w_l, dtype=float).reshape(ncell, nmode, self.xx.size)
+        self.psd_par = np.array(par_l, dtype=float).reshape(ncell, nmode, 4) if device_psd else None
+        self.lam = np.array([a[0] for a in meta])
+        self.rhop = np.array([a[1] for a in meta])
+        self.gf = np.array([a[2] for a in meta])
+        self.rLow = np.array([a[3] for a in meta])
+        self.rUp = np.array([a[4] for a in meta])
+        self.reff0 = None if device_psd else np.array([a[5] for a in meta]).reshape(ncell, nmode)
+
+    def _scan_cells(self, params, radind, lambarr, rh_used, part_m, water_m, want, trivial, device_psd, mr_l, w_l, par_l, meta):
+        """The lambda / RH loops of dointegration.fun (:811-889): per-cell refractive indices and size-distribution inputs."""
         for li, lam in enumerate(lambarr):
             if want is not None and not any(c[0] == li for c in want):
                 continue
@@ -481,16 +496,6 @@ class BinPlan(object):
                 self.cells.append((li, rhi))
                 mr_l.append([complex(a, b) for a, b in zip(mr, mi)])
                 meta.append((lam, rhop, gf, rLow, rUp, None if reff_mass0 is None else list(reff_mass0)))
-        ncell, nmode = len(self.cells), len(self.fracs)
-        self.m = np.array(mr_l, dtype=np.complex128).reshape(ncell, self.nri)
-        self.w = None if device_psd else np.array(w_l, dtype=float).reshape(ncell, nmode, self.xx.size)
-        self.psd_par = np.array(par_l, dtype=float).reshape(ncell, nmode, 4) if device_psd else None
-        self.lam = np.array([a[0] for a in meta])
-        self.rhop = np.array([a[1] for a in meta])
-        self.gf = np.array([a[2] for a in meta])
-        self.rLow = np.array([a[3] for a in meta])
-        self.rUp = np.array([a[4] for a in meta])
-        self.reff0 = None if device_psd else np.array([a[5] for a in meta]).reshape(ncell, nmode)
 
     # ---- flatten to GPU tasks
     def tasks(self):

@@ -60,24 +60,42 @@ def getWaterM():
     return data
 
 
-_growth_memo = {}
+_growth_memo = None      # dict while a growth_memo() scope is open, else None (plain evaluation)
+
+
+class growth_memo(object):
+    """Scope in which humidityGrowth remembers its results.  The humidified size of a dry size does not depend on the
+    wavelength, while the table build asks for it in every (wavelength, RH) cell of a bin (3 x 10,980 calls for optics_SS):
+    BinPlan opens this scope around its cell loop.  The memo lives only inside the scope, so a caller that edits the
+    parameter dict between two table builds never sees stale values."""
+
+    def __enter__(self):
+        global _growth_memo
+        self._outer = _growth_memo
+        _growth_memo = {} if _growth_memo is None else _growth_memo
+        return self
+
+    def __exit__(self, *exc):
+        global _growth_memo
+        _growth_memo = self._outer
+        return False
 
 
 def humidityGrowth(params, siz0, rh, allrh):
-    """Humidified size of a dry size siz0 at relative humidity rh (particleparams.py:85-108).  The result does not depend
-    on the wavelength, while the table build asks for it in every (wavelength, RH) cell: memoised per (params object, dry
-    size, RH) -- same arithmetic, evaluated once."""
+    """Humidified size of a dry size siz0 at relative humidity rh (particleparams.py:85-108); same arithmetic as the
+    reference, evaluated once per (parameter dict, dry size, RH) inside a growth_memo() scope."""
+    memo = _growth_memo
+    if memo is None:
+        return _humidityGrowth(params, siz0, rh, allrh)
     key = (id(params), siz0, rh)
     try:
-        hit = _growth_memo.get(key)
+        hit = memo.get(key)
     except TypeError:          # unhashable size (array): no memo
         return _humidityGrowth(params, siz0, rh, allrh)
     if hit is not None and hit[0] is params and hit[1] is allrh:
         return hit[2]
     val = _humidityGrowth(params, siz0, rh, allrh)
-    if len(_growth_memo) > 65536:
-        _growth_memo.clear()
-    _growth_memo[key] = (params, allrh, val)
+    memo[key] = (params, allrh, val)
     return val
 
 
