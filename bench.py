@@ -476,7 +476,7 @@ def main():
         "data": "su.json parameters; OPAC sulfate + HITRAN water refractive indices (tests/golden/hostlogic.npz)",
         "config": {"workload": "optics_SU dense table build: 1 bin x 4459 sizes x 61 lambda x 36 RH = 2196 cells, 371 angles, "
                                "then 129 GSF moments x 6 per cell", "cells_per_gpu": ncell, "nx": nx, "nang": NANG,
-                   "l2_policy": "inputs larger than L2 per step: 78 MB weights + 2.9 GB coefficient stream + 0.66 GB partial Gram blocks re-written every step",
+                   "l2_policy": "inputs larger than L2 per step: 78 MB weights + 2.9 GB coefficient stream + 0.62 GB partial Gram blocks re-written every step",
                    "parallelism": "cells sharded, %d rank(s), gather to rank 0: %s (overlapped with the next step, complete inside the timed region)"
                                   % (world, {"peer": "copy-engine puts into rank 0's IPC-mapped buffer over NVLink (gm_peer_put)",
                                              "store": "P2P stores of k_finalize / k_gsf into rank 0's IPC-mapped buffer",
