@@ -236,7 +236,14 @@ def main():
     if world > 1:
         import torch.distributed as td
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        td.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        # control plane (barrier, timing exchange, IPC handle broadcast): NCCL; GEOSMIE_BENCH_CONTROL=gloo is an experiment that
+        # keeps NCCL out of the process entirely (the rows then travel over the peer-memory gather only)
+        control = os.environ.get("GEOSMIE_BENCH_CONTROL", "nccl")
+        if control == "gloo":
+            td.init_process_group("gloo", rank=rank, world_size=world)
+        else:
+            td.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    ctrl_dev = torch.device("cpu") if (world > 1 and os.environ.get("GEOSMIE_BENCH_CONTROL", "nccl") == "gloo") else dev
 
     plan = build_su_plan()
     ang = _angles()
@@ -276,8 +283,10 @@ def main():
     nscal, nph, nco = ncell * _lib.GM_NSCAL, ncell * 4 * NANG, ncell * 6 * 129
     if world > 1:
         from geosmie_b200 import dist
-        comm = dist.Comm(rank, world, device=local)
+        comm = dist.Comm(rank, world, device=local, backend="gloo" if ctrl_dev.type == "cpu" else None)
         gather_mode = os.environ.get("GEOSMIE_GATHER", "peer")
+        if ctrl_dev.type == "cpu" and gather_mode == "nccl":
+            raise SystemExit("GEOSMIE_BENCH_CONTROL=gloo has no NCCL gather: use GEOSMIE_GATHER=peer|store|off")
         if gather_mode == "off":             # diagnostic: independent replicas, nothing leaves the GPU
             pass
         elif gather_mode in ("peer", "store"):
@@ -392,7 +401,7 @@ def main():
         barrier()
         ms = e0.elapsed_time(e1)
         if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            t = torch.tensor([ms], dtype=torch.float64, device=ctrl_dev)
             every = [torch.zeros_like(t) for _ in range(world)]
             td.all_gather(every, t)
             per_rank_ms.append([float(x.item()) / steps for x in every])

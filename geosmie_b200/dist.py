@@ -28,9 +28,10 @@ class Comm(object):
         self.torch, self.td = torch, td
         self.rank, self.world = rank, world
         self.backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
-        self.device = torch.device("cuda", device) if self.backend == "nccl" else torch.device("cpu")
-        if self.backend == "nccl":
-            torch.cuda.set_device(self.device)
+        self.device = torch.device("cuda", device) if self.backend == "nccl" else torch.device("cpu")   # device of the control tensors
+        self.gpu = device if (device is not None and torch.cuda.is_available()) else None                # GPU index of this rank
+        if self.gpu is not None:
+            torch.cuda.set_device(self.gpu)
         self._own = False
         self._peer, self._peer_failed = None, False
         if not td.is_initialized():
@@ -51,9 +52,9 @@ class Comm(object):
 
     def peer_gather(self, seg_bytes, nslot=1, handle=None):
         """A PeerGather (rank 0's buffer mapped by every rank through CUDA IPC) with segments of at least `seg_bytes`, or
-        None when the exchange runs on gloo, is switched off (GEOSMIE_GATHER=nccl) or could not be set up on every rank
+        None when there is no GPU (gloo tests on CPU), it is switched off (GEOSMIE_GATHER=nccl) or could not be set up on every rank
         (then the NCCL collectives below are used: still a GPU path)."""
-        if self.backend != "nccl" or os.environ.get("GEOSMIE_GATHER", "peer") == "nccl" or self._peer_failed:
+        if self.gpu is None or os.environ.get("GEOSMIE_GATHER", "peer") == "nccl" or self._peer_failed:
             return None
         pg = self._peer
         if pg is not None and pg.seg >= seg_bytes and pg.nslot >= nslot:
@@ -84,7 +85,7 @@ class Comm(object):
         nmax = max(counts)
         pg = self.peer_gather(nmax * width * 8) if nmax * width else None
         if pg is not None:
-            stage = torch.from_numpy(rows).to(self.device) if rows.size else None
+            stage = torch.from_numpy(rows).to(torch.device("cuda", self.gpu)) if rows.size else None
             if stage is not None:
                 pg.put(0, stage.data_ptr(), rows.nbytes)
             pg.complete()                                       # every rank's rows have landed on rank 0
@@ -137,7 +138,7 @@ class PeerGather(object):
     def __init__(self, comm, seg_bytes, nslot=1, handle=None):
         from . import _lib
         self.comm = comm
-        self.h = handle or _lib.Handle.get(comm.device.index)
+        self.h = handle or _lib.Handle.get(comm.gpu)
         self.seg = (int(seg_bytes) + 255) // 256 * 256
         self.nslot = int(nslot)
         self.base = None
