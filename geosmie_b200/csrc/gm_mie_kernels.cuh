@@ -176,6 +176,9 @@ struct CoeffArgs {
 #ifndef GM_COEFF_TPC
 #define GM_COEFF_TPC 1
 #endif
+#ifndef GM_COEFF_SHORT_START
+#define GM_COEFF_SHORT_START 0
+#endif
 #if GM_COEFF_TPC == 1
 #define GM_COEFF_TASK_LOOP const int task = blockIdx.y;
 #define GM_COEFF_NEXT_TASK return
@@ -209,7 +212,15 @@ __global__ void __launch_bounds__(128, GM_COEFF_MINB) k_coeff(CoeffArgs A) {
   }
   const bool act = valid && (MODE == 1 || A.dense || any);
   const double2 z = make_double2(mzv.x * xi, mzv.y * xi);                     // mie_coeffs.py:96
+#if GM_COEFF_SHORT_START
+  // experiment (default off): start the downward recurrence 4 + ceil(2.5 |z|) orders (at most the reference's 16) above
+  // max(nmax, |z|).  The error of D_n from starting with D = 0 falls by ~(|z| / 2j)^2 per order, so for |z| << 1 three to four
+  // orders already give D_n to 1 ulp (profiles/r01k_coeff_start_offset_study.txt); the reference always takes 16 (mie_coeffs.py:101).
+  const double zabs = sqrt(fma(z.x, z.x, z.y * z.y));
+  const int nmx = (act && MODE != 2) ? (int)rint(fmax((double)nm, zabs) + fmin(16.0, 4.0 + ceil(2.5 * zabs))) : 0;
+#else
   const int nmx = (act && MODE != 2) ? (int)rint(fmax((double)nm, sqrt(fma(z.x, z.x, z.y * z.y))) + 16.0) : 0;  // mie_coeffs.py:101
+#endif
   const int J = __reduce_max_sync(0xffffffffu, nmx);
   int rows = 0;
   if (TABLE) {
