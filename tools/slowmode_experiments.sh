@@ -4,13 +4,29 @@
 #
 #   (here)      make -C geosmie_b200/csrc && tools/slowmode_experiments.sh build      # variant library with -DGM_COEFF_TPC=4
 #   (GPU box)   gpurun --gpus 4 --timeout 400 -- 'tools/slowmode_experiments.sh run 4'
+#   (GPU box)   gpurun --timeout 400 -- 'tools/slowmode_experiments.sh perf'          # 1 GPU: parity + step time of the k_coeff variants
 set -u
 cd "$(dirname "$0")/.."
 if [ "${1:-}" = "build" ]; then
   mkdir -p tools/variants
   (cd geosmie_b200/csrc && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared \
      -DGM_COEFF_TPC=4 -o ../../tools/variants/lib_tpc4.so gm_api.cu gm_gsf.cu gm_bands.cu gm_peer.cu) && echo "built tools/variants/lib_tpc4.so"
+  (cd geosmie_b200/csrc && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared \
+     -DGM_COEFF_SHORT_START=1 -o ../../tools/variants/lib_short.so gm_api.cu gm_gsf.cu gm_bands.cu gm_peer.cu) && echo "built tools/variants/lib_short.so"
   exit $?
+fi
+if [ "${1:-}" = "perf" ]; then
+  # 1 GPU: parity of the k_coeff variants (whole GPU suite through the variant library) and their step times
+  for L in geosmie_b200/libgeosmie_b200.so tools/variants/lib_tpc4.so tools/variants/lib_short.so; do
+    [ -f $L ] || continue
+    echo "== $L"
+    GEOSMIE_B200_LIB=$L timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -1
+    GEOSMIE_B200_LIB=$L timeout 120 python bench.py --no-cpu-baseline --steps 10 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); k=d['roofline']['kernel_ms_per_step']
+print('step %.3f e2e %.3f k_coeff %.3f k_gram %.3f sum+eval %.3f' % (d['ms_per_step'], d['e2e']['ms_per_step'], k['k_coeff'], k['k_gram'], k['k_gram_sum_eval']))"
+  done
+  exit 0
 fi
 N=${2:-4}
 mkdir -p gpurun_out
