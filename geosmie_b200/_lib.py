@@ -405,7 +405,7 @@ class Table:
         check(self.lib.gm_table_last_kernel_ms(self.t, C.byref(a), C.byref(b), C.byref(c)))
         ms, n = np.zeros(8), np.zeros(8, dtype=np.int32)
         check(self.lib.gm_table_last_kernel_ms_ex(self.t, ptr(ms), ptr(n)))
-        names = ("k_coeff", "k_contract", "k_finalize", "k_gram", "k_gram_sum_eval")
+        names = ("k_coeff", "k_contract", "k_finalize", "k_gram", "k_gram_sum_eval", "k_small")
         out = {"coeff": a.value, "contract": b.value, "finalize": c.value}
         out.update({k: float(v) for k, v in zip(names, ms)})
         out["launches"] = dict(zip(names, n.tolist()))

@@ -10,6 +10,7 @@
 #include "gm_coated.cuh"
 #include "gm_psd.cuh"
 #include "gm_gram.cuh"
+#include "gm_small.cuh"
 
 #ifndef GM_HIO_MIN_BATCHES
 #define GM_HIO_MIN_BATCHES 3     // host-buffer calls: batches whose H2D / D2H copies are pipelined against the kernels (optics_SU e2e, equal batches: 2 -> 3.92, 3 -> 3.72, 4 -> 3.87, 6 -> 4.1 ms)
@@ -22,6 +23,10 @@
 #define GM_GRAM_SLOW0 1.0        // cost weight of class 0 / class 1 work items relative to their DMMA count.  Alone they run at 0.42 / 0.56 of
 #define GM_GRAM_SLOW1 1.0        // the DMMA peak against 0.76-0.84 for the others (tools/gram_class_probe.py), but weighting them 1.85 / 1.4
                                  // only made their task ranges shorter: optics_SU k_gram 1.249 ms against 1.197 ms (1.0 / 1.0)
+#endif
+#ifndef GM_SMALL_SEG0
+#define GM_SMALL_SEG0 16         // k_small: particle groups per work item (warp), class 0 (max nmax <= 4) / class 1 (max nmax <= 8)
+#define GM_SMALL_SEG1 8
 #endif
 #ifndef GM_EVAL_CTAS_PER_SM
 #define GM_EVAL_CTAS_PER_SM 2    // k_gram_eval: CTAs (angle block x task range) per SM
@@ -86,7 +91,7 @@ extern "C" int gm_destroy(gm_handle_t h) {
   cudaSetDevice(h->device);
   for (auto& b : h->ws) b.release();
   for (DevBuf* b : {&h->scratch_coef, &h->scratch_gact, &h->scratch_scal_part, &h->scratch_part, &h->scratch_g_hpart, &h->scratch_g_hsum,
-                    &h->scratch_wphase, &h->scratch_wscal})
+                    &h->scratch_wphase, &h->scratch_wscal, &h->scratch_taskc})
     b->release();
   h->gsf_nodes.release();
   h->gsf_table.release();
@@ -205,10 +210,11 @@ struct Groups {
 };
 
 struct DevGroups {
-  DevBuf x, nmax, gboff, gk4, grow, psi, chi;
+  DevBuf x, xinv, nmax, gboff, gk4, grow, psi, chi;
   int upload(const Groups& G, const double* hx, const int32_t* hnmax, cudaStream_t st) {
     int rc;
     if ((rc = x.ensure(sizeof(double) * G.nx))) return rc;
+    if ((rc = xinv.ensure(sizeof(double) * G.nx))) return rc;
     if ((rc = nmax.ensure(sizeof(int) * G.nx))) return rc;
     if ((rc = gboff.ensure(sizeof(long long) * G.ngroup))) return rc;
     if ((rc = gk4.ensure(sizeof(int) * G.ngroup))) return rc;
@@ -225,7 +231,7 @@ struct DevGroups {
     return GM_OK;
   }
   void release() {
-    x.release(); nmax.release(); gboff.release(); gk4.release(); grow.release(); psi.release(); chi.release();
+    x.release(); xinv.release(); nmax.release(); gboff.release(); gk4.release(); grow.release(); psi.release(); chi.release();
   }
 };
 
@@ -373,6 +379,7 @@ struct gm_table_s {
   std::vector<int32_t> hnmax;
   DevBuf T, cost, dr, psd_par, psd_frac;
   DevBuf g_list, g_skip, g_desc, g_items;   // Gram path (gm_gram.cuh)
+  DevBuf s_segs, s_big;                      // fused small-class path (gm_small.cuh): work-item segments, groups left to k_coeff
   DevBuf c_ab, c_scratch, c_soff, c_aboff, c_ratio;   // coated-sphere table path
   // fused GSF stage (gm_table_set_gsf): moments of every finished batch are expanded and downloaded behind the kernels
   std::vector<double> gsf_ang;
@@ -393,10 +400,10 @@ struct gm_table_s {
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // host-buffer calls: copies pipelined against the kernels
   std::vector<cudaEvent_t> io_events;
   std::vector<cudaEvent_t> evpool;   // pairs of events recorded around every launch of the last run (timing mode)
-  std::vector<int> evkind;           // 0 coeff, 1 contract, 2 finalize, 3 gram, 4 gram_eval
+  std::vector<int> evkind;           // 0 coeff, 1 contract, 2 finalize, 3 gram, 4 gram_eval, 5 small
   size_t evused = 0;
-  double ms_coeff = 0, ms_contract = 0, ms_finalize = 0, ms_gram = 0, ms_gram_eval = 0;
-  int n_coeff = 0, n_contract = 0, n_finalize = 0, n_gram = 0, n_gram_eval = 0;
+  double ms_coeff = 0, ms_contract = 0, ms_finalize = 0, ms_gram = 0, ms_gram_eval = 0, ms_small = 0;
+  int n_coeff = 0, n_contract = 0, n_finalize = 0, n_gram = 0, n_gram_eval = 0, n_small = 0;
 };
 
 extern "C" int gm_table_create(gm_handle_t h, int nx, const double* x, const int32_t* nmax, int nang, const double* cos_theta,
@@ -436,6 +443,8 @@ extern "C" int gm_table_create(gm_handle_t h, int nx, const double* x, const int
   GM_LAUNCH_CHECK(h);
   k_pt_table<<<(GM_NANG_PAD + 127) / 128, 128, 0, st>>>(nang, t->cost.as<double>(), t->nrows, t->T.as<double>());
   GM_LAUNCH_CHECK(h);
+  k_xinv<<<(nx + 127) / 128, 128, 0, st>>>(nx, t->D.x.as<double>(), t->D.xinv.as<double>());
+  GM_LAUNCH_CHECK(h);
   GM_CUDA_TRY(cudaStreamSynchronize(st));
   *out = t;
   return GM_OK;
@@ -445,7 +454,7 @@ extern "C" int gm_table_destroy(gm_table_t t) {
   if (!t) return GM_OK;
   cudaSetDevice(t->h->device);
   t->D.release();
-  for (DevBuf* b : {&t->g_list, &t->g_skip, &t->g_desc, &t->g_items, &t->gsf_coef, &t->gsf_cnorm, &t->c_ab, &t->c_scratch, &t->c_soff, &t->c_aboff, &t->c_ratio, &t->dr, &t->psd_par, &t->psd_frac, &t->T, &t->cost, &t->chunk_start, &t->mz, &t->mrel, &t->out_scal, &t->out_phase, &t->stats, &t->q, &t->s12})
+  for (DevBuf* b : {&t->g_list, &t->g_skip, &t->g_desc, &t->g_items, &t->s_segs, &t->s_big, &t->gsf_coef, &t->gsf_cnorm, &t->c_ab, &t->c_scratch, &t->c_soff, &t->c_aboff, &t->c_ratio, &t->dr, &t->psd_par, &t->psd_frac, &t->T, &t->cost, &t->chunk_start, &t->mz, &t->mrel, &t->out_scal, &t->out_phase, &t->stats, &t->q, &t->s12})
     b->release();
   for (auto& e : t->evpool) cudaEventDestroy(e);
   for (auto& e : t->io_events) cudaEventDestroy(e);
@@ -507,8 +516,8 @@ extern "C" int gm_table_last_kernel_ms(gm_table_t t, double* a, double* b, doubl
   if (t->timing && t->evused) {
     GM_CUDA_TRY(cudaSetDevice(t->h->device));
     GM_CUDA_TRY(cudaStreamSynchronize(t->h->stream));
-    t->ms_coeff = t->ms_contract = t->ms_finalize = t->ms_gram = t->ms_gram_eval = 0;
-    t->n_coeff = t->n_contract = t->n_finalize = t->n_gram = t->n_gram_eval = 0;
+    t->ms_coeff = t->ms_contract = t->ms_finalize = t->ms_gram = t->ms_gram_eval = t->ms_small = 0;
+    t->n_coeff = t->n_contract = t->n_finalize = t->n_gram = t->n_gram_eval = t->n_small = 0;
     for (size_t i = 0; i + 1 < t->evused; i += 2) {
       float ms = 0;
       GM_CUDA_TRY(cudaEventElapsedTime(&ms, t->evpool[i], t->evpool[i + 1]));
@@ -517,26 +526,29 @@ extern "C" int gm_table_last_kernel_ms(gm_table_t t, double* a, double* b, doubl
       if (t->evkind[i] == 2) { t->ms_finalize += ms; t->n_finalize++; }
       if (t->evkind[i] == 3) { t->ms_gram += ms; t->n_gram++; }
       if (t->evkind[i] == 4) { t->ms_gram_eval += ms; t->n_gram_eval++; }
+      if (t->evkind[i] == 5) { t->ms_small += ms; t->n_small++; }
     }
   }
   if (a) *a = t->ms_coeff;
-  if (b) *b = t->ms_contract + t->ms_gram + t->ms_gram_eval;   // the whole angular stage
+  if (b) *b = t->ms_contract + t->ms_gram + t->ms_gram_eval + t->ms_small;   // the whole angular stage (k_small: fused with its coefficients)
   if (c) *c = t->ms_finalize;
   return GM_OK;
 }
 
-// per-kernel split of the last run: ms[0..4] = k_coeff, k_contract, k_finalize, k_gram, k_gram_sum + k_gram_eval;
+// per-kernel split of the last run: ms[0..5] = k_coeff, k_contract, k_finalize, k_gram, k_gram_sum + k_gram_eval, k_small;
 // n[0..4] = event-bracketed launch groups of each
 extern "C" int gm_table_last_kernel_ms_ex(gm_table_t t, double ms[8], int32_t n[8]) {
   int rc = gm_table_last_kernel_ms(t, nullptr, nullptr, nullptr);
   if (rc) return rc;
   if (ms) {
     ms[0] = t->ms_coeff; ms[1] = t->ms_contract; ms[2] = t->ms_finalize; ms[3] = t->ms_gram; ms[4] = t->ms_gram_eval;
-    ms[5] = ms[6] = ms[7] = 0;
+    ms[5] = t->ms_small;
+    ms[6] = ms[7] = 0;
   }
   if (n) {
     n[0] = t->n_coeff; n[1] = t->n_contract; n[2] = t->n_finalize; n[3] = t->n_gram; n[4] = t->n_gram_eval;
-    n[5] = n[6] = n[7] = 0;
+    n[5] = t->n_small;
+    n[6] = n[7] = 0;
   }
   return GM_OK;
 }
@@ -622,6 +634,10 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
     bstart.push_back(ntask);
   }
   const bool use_gram = !per_particle && !(flags & GM_F_NO_GRAM) && !G.glist.empty();
+  // fused coefficient + Gram kernel for the groups with max nmax <= 8 (gm_small.cuh): homogeneous spheres, one PSD mode
+  static const bool small_off = getenv("GEOSMIE_NO_SMALL") != nullptr;     // diagnostics: the round-1 path (k_coeff + k_gram) for every class
+  const bool use_small = use_gram && nmode == 1 && !d_core_ratio && !small_off && G.cls_begin[2] > 0;
+  std::vector<SmallSeg> small_segs;
   const int ndirect = use_gram ? G.ndirect : G.ngroup;
   // chunks of the per-angle contraction: enough CTAs to fill the machine ~8x over, cost-balanced by the k4 steps of the
   // groups it handles (groups taken by the Gram path cost nothing here); a chunk never holds more groups than the smem metadata
@@ -680,6 +696,7 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
       for (int c = 0; c <= GM_GRAM_MAX_TG; ++c) {
         const int nc = G.cls_begin[c + 1] - G.cls_begin[c];
         ccost[c] = (double)nc * (dmma_per_group(c) + 48.0) * (c <= 1 ? slow[c] : 1.0);   // DMMA issue slots per task (+ ring handling per group)
+        if (use_small && c <= 1) continue;   // not k_gram's work
         total += ccost[c] * nt;
       }
       const double target = std::max(total / (h->sm_count * 6.0), 12000.0);
@@ -687,6 +704,31 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
       for (int c = 0; c <= GM_GRAM_MAX_TG; ++c) {
         const int nc = G.cls_begin[c + 1] - G.cls_begin[c];
         if (nc == 0) continue;
+        if (use_small && c <= 1) {
+          // classes 0 / 1 are evaluated AND reduced by k_small: one descriptor whose "teams" are the segments (work items) of the
+          // class; no k_gram work item.  The segment list does not depend on the batch size (classes 0, 1 come first in hstride).
+          const int per = c == 0 ? GM_SMALL_SEG0 : GM_SMALL_SEG1;
+          const int nseg = std::max(1, std::min(GM_SMALL_MAXSEG, (nc + per - 1) / per));
+          GramDesc d;
+          d.tg = c;
+          d.nteam = nseg;
+          d.gbegin = G.cls_begin[c];
+          d.gend = G.cls_begin[c + 1];
+          d.hoff = P.hstride;
+          if (plans.empty())
+            for (int k = 0; k < nseg; ++k) {
+              SmallSeg sgm;
+              sgm.cls = c;
+              sgm.gbegin = G.cls_begin[c] + (int)((long long)nc * k / nseg);
+              sgm.gend = G.cls_begin[c] + (int)((long long)nc * (k + 1) / nseg);
+              sgm.seg = k;
+              sgm.hoff = d.hoff;
+              small_segs.push_back(sgm);
+            }
+          P.hstride += (long long)nseg * 4 * (c == 0 ? 16 : 64);
+          all_desc.push_back(d);
+          continue;
+        }
         const int nteam = c <= 1 ? 12 : c == 2 ? 6 : c <= 4 ? 3 : 1;   // GramCfg<c>::NTEAM
         int nsplit = 1, tpc = 1;
         if (ccost[c] > 1.5 * target) nsplit = std::min(nc, (int)std::lround(ccost[c] / target));
@@ -743,6 +785,19 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
       return rc;
     GM_CUDA_TRY(cudaMemcpyAsync(t->g_desc.p, all_desc.data(), sizeof(GramDesc) * all_desc.size(), cudaMemcpyHostToDevice, st));
     GM_CUDA_TRY(cudaMemcpyAsync(t->g_items.p, all_items.data(), sizeof(GramItem) * all_items.size(), cudaMemcpyHostToDevice, st));
+  }
+  std::vector<int> big_groups;
+  if (use_small) {
+    std::vector<unsigned char> is_small(G.ngroup, 0);
+    for (int k = G.cls_begin[0]; k < G.cls_begin[2]; ++k) is_small[G.glist[k]] = 1;
+    for (int g = 0; g < G.ngroup; ++g)
+      if (!is_small[g]) big_groups.push_back(g);
+    if ((rc = t->s_segs.ensure(sizeof(SmallSeg) * small_segs.size())) || (rc = t->s_big.ensure(sizeof(int) * std::max<size_t>(1, big_groups.size()))) ||
+        (rc = t->h->scratch_taskc.ensure(sizeof(double2) * 2 * (size_t)tb)))
+      return rc;
+    GM_CUDA_TRY(cudaMemcpyAsync(t->s_segs.p, small_segs.data(), sizeof(SmallSeg) * small_segs.size(), cudaMemcpyHostToDevice, st));
+    if (!big_groups.empty())
+      GM_CUDA_TRY(cudaMemcpyAsync(t->s_big.p, big_groups.data(), sizeof(int) * big_groups.size(), cudaMemcpyHostToDevice, st));
   }
   if ((rc = t->h->scratch_coef.ensure(per_task_bytes * tb)) || (rc = t->h->scratch_gact.ensure((size_t)tb * G.ngroup)) ||
       (rc = t->h->scratch_scal_part.ensure(sizeof(double) * (size_t)tb * nmode * G.ngroup * GM_NSCAL)) ||
@@ -835,11 +890,49 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
       A.ab = t->c_ab.as<double4>();
       A.ab_stride = t->c_nab;
       k_coeff<2><<<dim3((G.ngroup + 3) / 4, (nt + GM_COEFF_TPC - 1) / GM_COEFF_TPC), 128, 0, st>>>(A);
+    } else if (use_small) {
+      A.gsel = t->s_big.as<int>();
+      A.nsel = (int)big_groups.size();
+      if (A.nsel > 0) k_coeff<0><<<dim3((A.nsel + 3) / 4, (nt + GM_COEFF_TPC - 1) / GM_COEFF_TPC), 128, 0, st>>>(A);
     } else {
       k_coeff<0><<<dim3((G.ngroup + 3) / 4, (nt + GM_COEFF_TPC - 1) / GM_COEFF_TPC), 128, 0, st>>>(A);
     }
     GM_LAUNCH_CHECK(h);
     if ((rc = ev_mark(t, 0))) return rc;
+    if (use_small) {
+      SmallArgs SA;
+      memset(&SA, 0, sizeof(SA));
+      SA.nx = G.nx;
+      SA.ngroup = G.ngroup;
+      SA.ntask = nt;
+      SA.nseg = (int)small_segs.size();
+      SA.segs = t->s_segs.as<SmallSeg>();
+      SA.glist = t->g_list.as<int>();
+      SA.x = A.x;
+      SA.xinv = t->D.xinv.as<double>();
+      SA.nmax = A.nmax;
+      SA.psi = A.psi;
+      SA.chi = A.chi;
+      SA.gboff = A.gboff;
+      SA.mz = A.mz;
+      SA.mrel = A.mrel;
+      SA.mzinv = t->h->scratch_taskc.as<double2>();
+      SA.mrinv = SA.mzinv + tb;
+      SA.wphase = A.wphase;
+      SA.wscal = A.wscal;
+      SA.dense = A.dense;
+      SA.ntab = A.ntab;
+      SA.hpart = t->h->scratch_g_hpart.as<double>();
+      SA.hstride = P->hstride;
+      SA.scal_part = A.scal_part;
+      SA.stats = A.stats;
+      if ((rc = ev_mark(t, 5))) return rc;
+      k_task_prep<<<(nt + 127) / 128, 128, 0, st>>>(nt, SA.mz, SA.mrel, const_cast<double2*>(SA.mzinv), const_cast<double2*>(SA.mrinv));
+      GM_LAUNCH_CHECK(h);
+      k_small<<<dim3((nt + GM_SMALL_WARPS - 1) / GM_SMALL_WARPS, SA.nseg), GM_SMALL_WARPS * 32, 0, st>>>(SA);
+      GM_LAUNCH_CHECK(h);
+      if ((rc = ev_mark(t, 5))) return rc;
+    }
 
     ContractArgs C;
     memset(&C, 0, sizeof(C));

@@ -67,7 +67,7 @@ struct gm_handle_s {
   size_t coef_budget_bytes = (size_t)4 << 30;  // coefficient staging buffer per gm_table_run batch (optics_SU dense: 2.9 GB = one batch)
   // per-run scratch of gm_table_run* (coefficient stream, partial sums, weights): grow-only and shared by all tables of the
   // handle, so that building one table per size bin does not pay a multi-GB cudaMalloc / cudaFree per bin
-  DevBuf scratch_coef, scratch_gact, scratch_scal_part, scratch_part, scratch_g_hpart, scratch_g_hsum, scratch_wphase, scratch_wscal;
+  DevBuf scratch_coef, scratch_gact, scratch_scal_part, scratch_part, scratch_g_hpart, scratch_g_hsum, scratch_wphase, scratch_wscal, scratch_taskc;
   // GSF constants (Gauss nodes, interpolation brackets, generalized spherical functions) cached per angle grid
   DevBuf gsf_nodes, gsf_table, gsf_alt, gsf_raw;
   std::vector<double> gsf_key;

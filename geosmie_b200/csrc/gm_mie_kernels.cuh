@@ -73,6 +73,12 @@ __global__ void __launch_bounds__(128) k_bessel(int nx, const double* __restrict
 #undef BIDX
 }
 
+// 1 / x per particle (the quotient k_coeff forms per task; k_small reads it)
+__global__ void __launch_bounds__(128) k_xinv(int nx, const double* __restrict__ x, double* __restrict__ xinv) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nx) xinv[i] = 1.0 / x[i];
+}
+
 // caller-supplied J_{k+1/2}(x), Y_{k+1/2}(x) -> psi, chi (mie_coeffs.py:106-112; psi_0 = sin x, chi_0 = cos x)
 __global__ void __launch_bounds__(128) k_bessel_from_jy(int nx, const double* __restrict__ x, const int* __restrict__ nmax,
                                                         const long long* __restrict__ gboff, const long long* __restrict__ off,
@@ -162,6 +168,8 @@ struct CoeffArgs {
   int ntask;                  // tasks of this launch (bound of the task loop when GM_COEFF_TPC > 1)
   const double2* ntab;        // [n] = ((2n+1)/(n(n+1)), n(n+2)/(n+1)): the order-dependent factors of mie_props_raw, read with a
                               // warp-uniform index instead of two reciprocals per order
+  const int* gsel;            // nullable: the kernel works on the groups gsel[0..nsel) only (the others belong to k_small)
+  int nsel;
 };
 
 // MODE 0: DMMA group layout (c+ = (a+b) f_n sqrt(w), c- = (a-b) f_n sqrt(w)); MODE 1: natural a_n, b_n;
@@ -189,7 +197,11 @@ struct CoeffArgs {
 #endif
 template <int MODE>
 __global__ void __launch_bounds__(128, GM_COEFF_MINB) k_coeff(CoeffArgs A) {
-  const int g = blockIdx.x * 4 + (threadIdx.x >> 5);
+  int g = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (A.gsel) {
+    if (g >= A.nsel) return;
+    g = A.gsel[g];
+  }
   if (g >= A.ngroup) return;
   const int lane = threadIdx.x & 31;
   const int i = g * 32 + lane;
@@ -341,11 +353,13 @@ __global__ void __launch_bounds__(128, GM_COEFF_MINB) k_coeff(CoeffArgs A) {
         A.ab[abo + n - 1] = make_double4(an.x, an.y, bn.x, bn.y);
       }
     }
+#ifndef GM_COEFF_NOSTORE   // (diagnostic builds only: the kernel without its coefficient-stream stores)
     if (TABLE) {
       double* r = crow + (size_t)(n - 1) * GM_SB;
       *reinterpret_cast<double2*>(r) = cp;
       *reinterpret_cast<double2*>(r + 64) = cm;
     }
+#endif
   }
   // mie_props.py:44-68
   // (divisions by y^2 and qsca as multiplications by reciprocals: <= 2 ulp from the reference's quotients)

@@ -57,12 +57,11 @@ def getXArrCarma(minx, maxx, nbinperdecade):
     cpi = 4. / 3. * np.pi
     rvolmin = cpi * rMin ** 3.
     vrfact = ((3. / 2. / np.pi / (rmRat + 1)) ** (1. / 3.)) * (rmRat ** (1. / 3.) - 1.)
-    r, dr = [], []
-    for i in range(int(nbin)):
-        rvol = rvolmin * rmRat ** i
-        r.append((rvol / cpi) ** (1. / 3.))
-        dr.append(vrfact * (rvol) ** (1. / 3.))
-    return np.array(r), np.array(dr)
+    # per point: rvol = rvolmin * rmRat ** i, r = (rvol / cpi) ** (1/3), dr = vrfact * rvol ** (1/3) -- as Python floats (the same
+    # libm pow and IEEE products as the reference's numpy scalars, without their per-operation overhead)
+    rvolmin, rmRat, vrfact, third = float(rvolmin), float(rmRat), float(vrfact), 1. / 3.
+    rvol = [rvolmin * rmRat ** i for i in range(int(nbin))]
+    return np.array([(v / cpi) ** third for v in rvol]), np.array([vrfact * v ** third for v in rvol])
 
 
 def initializeXarr(params, radind, minlam, maxlam):
@@ -398,30 +397,39 @@ def bins_of(params):
     raise ValueError("unknown psd type %r" % t)
 
 
-def psd_parameters(params, radind, onerh, rh, lam):
-    """The per-cell scalars of calculatePSD (dointegration.py:539-664) without its O(nx) array work: what the device
-    kernel k_psd needs to generate the number weights.  Returns (kind, par [nmode][4], rLow, rUp)."""
+def psd_parameters_rh(params, radind, onerh, rh):
+    """The humidity-dependent scalars of calculatePSD (dointegration.py:539-664): everything psd_parameters needs except the
+    wavelength.  Returns (kind, modes, rLow, rUp); modes[k] = the lengths [m] of mode k that get multiplied by 2 pi / lambda
+    (lognorm: r_mode, r_min, r_max, then ln sigma as is; ss: r_min_use, r_max_use, r_min / r_min_use as they are)."""
     pparam = params['psd']['params']
     psdtype = params['psd']['type']
     rparams = params['rhDep']
-    xconv = 2 * np.pi / lam
     if psdtype == 'lognorm':
         rmodes = [pp.humidityGrowth(rparams, r0, onerh, rh) for r0 in pparam['r0'][radind]]
         rmaxs0 = list(pparam['rmax0'][radind])
         rmaxs = [pp.humidityGrowth(rparams, r, onerh, rh) for r in rmaxs0]
         rmins = list(pparam['rmin0'][radind])
         sig = pparam['sigma'][radind]
-        par = [[rmodes[k] * xconv, rmins[k] * xconv, rmaxs[k] * xconv, np.log(sig[k])] for k in range(len(rmodes))]
-        return _lib.PSD_LOGNORM, par, rmins[0], rmaxs0[0]
+        return _lib.PSD_LOGNORM, [[rmodes[k], rmins[k], rmaxs[k], np.log(sig[k])] for k in range(len(rmodes))], rmins[0], rmaxs0[0]
     if psdtype == 'ss':
         rMinMaj, rMaxMaj = pparam['rMinMaj'][radind], pparam['rMaxMaj'][radind]
         rMinUse = pp.humidityGrowth(rparams, rMinMaj, onerh, rh)
         rMaxUse = pp.humidityGrowth(rparams, rMaxMaj, onerh, rh)
-        return _lib.PSD_SS, [[xconv, rMinUse, rMaxUse, rMinMaj / rMinUse]], rMinMaj, rMaxMaj
+        return _lib.PSD_SS, [[1.0, rMinUse, rMaxUse, rMinMaj / rMinUse]], rMinMaj, rMaxMaj
     if psdtype == 'du':
         lo, hi = pparam['rMinMaj'][radind], pparam['rMaxMaj'][radind]
-        return _lib.PSD_DU, [[xconv, a, b, 0.0] for a, b in zip(lo, hi)], lo[-1], hi[-1]
+        return _lib.PSD_DU, [[1.0, a, b, 0.0] for a, b in zip(lo, hi)], lo[-1], hi[-1]
     raise ValueError("unknown psd type %r" % psdtype)
+
+
+def psd_parameters(params, radind, onerh, rh, lam):
+    """The per-cell scalars of calculatePSD (dointegration.py:539-664) without its O(nx) array work: what the device
+    kernel k_psd needs to generate the number weights.  Returns (kind, par [nmode][4], rLow, rUp)."""
+    kind, modes, rLow, rUp = psd_parameters_rh(params, radind, onerh, rh)
+    xconv = 2 * np.pi / lam
+    if kind == _lib.PSD_LOGNORM:
+        return kind, [[m[0] * xconv, m[1] * xconv, m[2] * xconv, m[3]] for m in modes], rLow, rUp
+    return kind, [[xconv, m[1], m[2], m[3]] for m in modes], rLow, rUp
 
 
 class BinPlan(object):
@@ -456,6 +464,10 @@ class BinPlan(object):
         want = None if cells is None else set(cells)
         if device_psd and want:
             want |= {(li, 0) for (li, _) in want}      # reff_mass0 comes from the RH-index-0 cell of the same wavelength
+        if device_psd:
+            # the wavelength and the humidity enter the per-cell inputs separately: 61 + 36 evaluations instead of 61 x 36
+            self._scan_cells_separable(params, radind, lambarr, rh_used, part_m, water_m, want, trivial)
+            return
         with pp.growth_memo():
             self._scan_cells(params, radind, lambarr, rh_used, part_m, water_m, want, trivial, device_psd, mr_l, w_l, par_l, meta)
         ncell, nmode = len(self.cells), len(self.fracs)
@@ -468,6 +480,67 @@ class BinPlan(object):
         self.rLow = np.array([a[3] for a in meta])
         self.rUp = np.array([a[4] for a in meta])
         self.reff0 = None if device_psd else np.array([a[5] for a in meta]).reshape(ncell, nmode)
+
+    def _scan_cells_separable(self, params, radind, lambarr, rh_used, part_m, water_m, want, trivial):
+        """The lambda / RH loops of dointegration.fun (:811-889) for the device-PSD path, without a Python loop over cells.
+        Every per-cell input is a product of a wavelength-only and a humidity-only factor: n_0(lambda), n_water(lambda) and
+        2 pi / lambda on one side, the growth factor, rrat^3, the wet density and the grown mode radii on the other.  The
+        humidity-only scalars are evaluated with the reference's own scalar statements (one call per RH level), the outer
+        combination is the same IEEE multiply / add per element, so the result is bit-identical to the cell loop
+        (tests/test_host_logic.py, tests/test_live_reference.py)."""
+        lam = np.asarray(lambarr, dtype=float)
+        nl, nr = lam.size, len(rh_used)
+        rlist = [0] if trivial else list(range(nr))
+        # humidity-only part (getHumidRefractiveIndex :493-536 with a dummy index, psd_parameters_rh)
+        gf, r3, rhop, modes = [], [], [], []
+        kind = rLow = rUp = None
+        with pp.growth_memo():
+            for rhi in rlist:
+                _, _, g, rrat = getHumidRefractiveIndex(params, radind, rhi, rh_used, [0j], 0j)
+                kind, md, rLow, rUp = psd_parameters_rh(params, radind, rh_used[rhi], rh_used)
+                gf.append(g)
+                r3.append(rrat ** 3.)
+                rhop.append(rrat ** 3. * self.rhop0 + (1. - rrat ** 3.) * 1000.)
+                modes.append(md)
+        self.psd_kind = kind
+        gf, r3, rhop, modes = np.array(gf, dtype=float), np.array(r3, dtype=float), np.array(rhop, dtype=float), np.array(modes, dtype=float)
+        # wavelength-only part (:813-826): the stored -k is flipped, water is used as is
+        n0_re = np.stack([np.asarray(f[0](lam), dtype=float) for f in part_m], axis=1)            # [nl][nri]
+        n0_im = np.stack([-np.asarray(f[1](lam), dtype=float) for f in part_m], axis=1)
+        if trivial:
+            nw_re, nw_im = np.ones(nl), np.zeros(nl)
+        else:
+            nw_re, nw_im = np.asarray(water_m[0](lam), dtype=float), np.asarray(water_m[1](lam), dtype=float)
+        # n = n_w + (n_0 - n_w) rrat^3 component by component (a Python complex times a float is the same two products)
+        mre = nw_re[:, None, None] + (n0_re - nw_re[:, None])[:, None, :] * r3[None, :, None]       # [nl][nrh][nri]
+        mim = nw_im[:, None, None] + (n0_im - nw_im[:, None])[:, None, :] * r3[None, :, None]
+        xconv = 2 * np.pi / lam
+        nmode = modes.shape[1]
+        par = np.empty((nl, len(rlist), nmode, 4))
+        if kind == _lib.PSD_LOGNORM:
+            par[..., :3] = modes[None, :, :, :3] * xconv[:, None, None, None]
+            par[..., 3] = modes[None, :, :, 3]
+        else:
+            par[..., 0] = xconv[:, None, None]
+            par[..., 1:] = modes[None, :, :, 1:]
+        sel = np.ones((nl, len(rlist)), dtype=bool)
+        if want is not None:
+            sel[:] = False
+            for (li, rhi) in want:
+                if rhi in rlist:
+                    sel[li, rlist.index(rhi)] = True
+        li_idx, rj = np.nonzero(sel)                      # wavelength-major, RH-minor: the order of the reference's loops
+        ri_idx = np.asarray(rlist, dtype=np.int64)[rj]
+        self.cells = list(zip(li_idx.tolist(), ri_idx.tolist()))
+        self.m = (mre[li_idx, rj] + 1j * mim[li_idx, rj]).reshape(len(self.cells), self.nri)
+        self.w = None
+        self.psd_par = np.ascontiguousarray(par[li_idx, rj])
+        self.lam = lam[li_idx]
+        self.rhop = rhop[rj]
+        self.gf = gf[rj]
+        self.rLow = np.full(len(self.cells), rLow, dtype=float)
+        self.rUp = np.full(len(self.cells), rUp, dtype=float)
+        self.reff0 = None
 
     def _scan_cells(self, params, radind, lambarr, rh_used, part_m, water_m, want, trivial, device_psd, mr_l, w_l, par_l, meta):
         """The lambda / RH loops of dointegration.fun (:811-889): per-cell refractive indices and size-distribution inputs."""
