@@ -12,6 +12,7 @@ GM_NSCAL = 11
 S_W, S_X2W, S_X3W, S_X4W, S_QEXT, S_QSCA, S_QABS, S_QB, S_G, S_CSCA, S_CEXT = range(11)
 F_ELIDE_ZERO_WEIGHT = 1
 F_NO_GRAM = 2
+F_PHASE_ON_DEVICE = 4
 PSD_LOGNORM, PSD_SS, PSD_DU, PSD_NPAR = 1, 2, 3, 4
 
 _lib = None
@@ -49,6 +50,7 @@ SIGNATURES = {
     "gm_table_particles": (C.c_int, [vp, C.c_int, vp, vp, vp, vp]),
     "gm_table_last_stats": (C.c_int, [vp, vp]),
     "gm_table_set_timing": (C.c_int, [vp, C.c_int]),
+    "gm_table_fetch_normalized": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp]),
     "gm_table_last_kernel_ms": (C.c_int, [vp, c_dp, c_dp, c_dp]),
     "gm_table_last_kernel_ms_ex": (C.c_int, [vp, vp, vp]),
     "gm_gsf_expand": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int]),
@@ -87,7 +89,12 @@ def load():
                                "`make -C geosmie_b200/csrc` -- there is no CPU fallback" % path)
         lib = C.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
-            fn = getattr(lib, name)
+            try:
+                fn = getattr(lib, name)
+            except AttributeError:
+                if path != LIB_PATH:
+                    continue          # an experiment build made before the entry point existed; the in-tree library must have them all
+                raise
             fn.restype = res
             fn.argtypes = args
         _lib = lib
@@ -299,6 +306,18 @@ class Table:
             assert ws.shape == (ntask, nmode, self.nx)
         scal = np.empty((ntask, nmode, GM_NSCAL))
         phase = np.empty((ntask, 4, self.nang))
+        if wp.min() < 0.0:
+            # Signed number weights (the reference's non-monotonic 'du' grid makes getDR negative in places): the device folds
+            # sqrt(w_phase) into the coefficients, so w_phase must be >= 0 there (gm_table_run answers GM_EINVAL otherwise).  The
+            # sums are linear in w: phase = phase(w+) - phase(w-); the scalar sums take the signed per-mode weights as they are.
+            neg = wp < 0.0
+            wpos = np.where(neg, 0.0, wp)
+            check(self.lib.gm_table_run(self.t, ntask, ptr(mz), ptr(mrel), nmode, ptr(wpos), ptr(ws if ws is not None else wp),
+                                        self._flags(elide), ptr(scal), ptr(phase)))
+            wneg = np.where(neg, -wp, 0.0)
+            scal_n, phase_n = np.empty((ntask, 1, GM_NSCAL)), np.empty((ntask, 4, self.nang))
+            check(self.lib.gm_table_run(self.t, ntask, ptr(mz), ptr(mrel), 1, ptr(wneg), None, self._flags(True), ptr(scal_n), ptr(phase_n)))
+            return scal, phase - phase_n
         check(self.lib.gm_table_run(self.t, ntask, ptr(mz), ptr(mrel), nmode, ptr(wp), ptr(ws), self._flags(elide),
                                     ptr(scal), ptr(phase)))
         return scal, phase
@@ -339,9 +358,10 @@ class Table:
     def set_dr(self, dr):
         check(self.lib.gm_table_set_dr(self.t, ptr(f64(dr))))
 
-    def run_psd(self, mz, mrel, kind, params, frac, elide=False, out=None):
+    def run_psd(self, mz, mrel, kind, params, frac, elide=False, out=None, phase_on_device=False):
         """Weights generated on the device from per-(task, mode) parameters.  params [ntask][nmode][4], frac [ntask][nmode].
-        `out` = (scal, phase) caller-provided (e.g. pinned) arrays."""
+        `out` = (scal, phase) caller-provided (e.g. pinned) arrays.  phase_on_device=True: the raw phase sums are not downloaded
+        (returns (scal, None)); fetch_normalized() delivers the normalised phase matrix instead."""
         mz = np.ascontiguousarray(np.atleast_1d(mz), dtype=np.complex128)
         mrel = np.ascontiguousarray(np.atleast_1d(mrel), dtype=np.complex128)
         ntask = mz.size
@@ -349,11 +369,34 @@ class Table:
         nmode = params.shape[1]
         assert params.shape == (ntask, nmode, PSD_NPAR)
         frac = f64(np.broadcast_to(frac, (ntask, nmode)))
+        if phase_on_device:
+            scal = out[0] if out is not None else np.empty((ntask, nmode, GM_NSCAL))
+            check(self.lib.gm_table_run_psd(self.t, ntask, ptr(mz), ptr(mrel), nmode, int(kind), ptr(params), ptr(frac),
+                                            self._flags(elide) | F_PHASE_ON_DEVICE, ptr(scal), None))
+            self._last_psd_shape = (ntask, nmode)
+            self._last_ntask = ntask
+            return scal, None
         scal, phase = out if out is not None else (np.empty((ntask, nmode, GM_NSCAL)), np.empty((ntask, 4, self.nang)))
         check(self.lib.gm_table_run_psd(self.t, ntask, ptr(mz), ptr(mrel), nmode, int(kind), ptr(params), ptr(frac),
                                         self._flags(elide), ptr(scal), ptr(phase)))
         self._last_psd_shape = (ntask, nmode)
+        self._last_ntask = ntask
         return scal, phase
+
+    def fetch_normalized(self, ang_deg, out=None):
+        """dointegration.py:977-988 on the device-resident phase sums of the last run call: returns (p11, p12, p33, p34) [ntask][nang]
+        normalised to 2 / trapz(p11 sin(theta), theta) and pback4 [ntask][4].  `out` = four caller arrays (each C-contiguous,
+        ntask * nang doubles: e.g. slices of the final table arrays) to write the planes into."""
+        ntask = self._last_ntask
+        theta = np.radians(f64(ang_deg))
+        sint = np.sin(theta)
+        planes = out if out is not None else [np.empty((ntask, self.nang)) for _ in range(4)]
+        for a in planes:
+            assert a.flags["C_CONTIGUOUS"] and a.dtype == np.float64 and a.size == ntask * self.nang
+        pback4 = np.empty((ntask, 4))
+        check(self.lib.gm_table_fetch_normalized(self.t, ntask, ptr(theta), ptr(sint), ptr(planes[0]), ptr(planes[1]), ptr(planes[2]),
+                                                 ptr(planes[3]), ptr(pback4)))
+        return planes, pback4
 
     def get_weights(self):
         ntask, nmode = self._last_psd_shape

@@ -99,7 +99,10 @@ def fun(data, part, opfn, mode, useSolar, noIR):
             else:
                 val[:, 2, :] = (bw1 * val[:, 0, :] + bw2 * val[:, 2, :]) / (bw1 + bw2)
                 output[key] = val[:, 1:, :]
-            bandMeanM = bandMeanM[1:]          # (sic) sliced once per variable, as in the reference (:220)
+        # The reference drops the first band centre INSIDE the loop over the eight variables (bandaverage.py:220), leaves 11 of
+        # the 19 values for an 18-long wavelength variable and stops with a broadcast error when it writes the file: its GEOS5 mode
+        # cannot finish.  The evident intent -- the centre of the dropped band 0 goes once -- is what is done here.
+        bandMeanM = bandMeanM[1:]
     nc = ncio.Dataset(opfn, 'w')
     nc.createDimension('rh', nrh)
     nc.createDimension(lamNm, nbands)

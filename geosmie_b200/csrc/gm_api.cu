@@ -379,6 +379,7 @@ struct gm_table_s {
   std::vector<int32_t> hnmax;
   DevBuf T, cost, dr, psd_par, psd_frac;
   DevBuf g_list, g_skip, g_desc, g_items;   // Gram path (gm_gram.cuh)
+  DevBuf norm_planes, norm_ang;              // gm_table_fetch_normalized
   DevBuf s_segs, s_big;                      // fused small-class path (gm_small.cuh): work-item segments, groups left to k_coeff
   DevBuf c_ab, c_scratch, c_soff, c_aboff, c_ratio;   // coated-sphere table path
   // fused GSF stage (gm_table_set_gsf): moments of every finished batch are expanded and downloaded behind the kernels
@@ -454,7 +455,7 @@ extern "C" int gm_table_destroy(gm_table_t t) {
   if (!t) return GM_OK;
   cudaSetDevice(t->h->device);
   t->D.release();
-  for (DevBuf* b : {&t->g_list, &t->g_skip, &t->g_desc, &t->g_items, &t->s_segs, &t->s_big, &t->gsf_coef, &t->gsf_cnorm, &t->c_ab, &t->c_scratch, &t->c_soff, &t->c_aboff, &t->c_ratio, &t->dr, &t->psd_par, &t->psd_frac, &t->T, &t->cost, &t->chunk_start, &t->mz, &t->mrel, &t->out_scal, &t->out_phase, &t->stats, &t->q, &t->s12})
+  for (DevBuf* b : {&t->g_list, &t->g_skip, &t->g_desc, &t->g_items, &t->s_segs, &t->s_big, &t->norm_planes, &t->norm_ang, &t->gsf_coef, &t->gsf_cnorm, &t->c_ab, &t->c_scratch, &t->c_soff, &t->c_aboff, &t->c_ratio, &t->dr, &t->psd_par, &t->psd_frac, &t->T, &t->cost, &t->chunk_start, &t->mz, &t->mrel, &t->out_scal, &t->out_phase, &t->stats, &t->q, &t->s12})
     b->release();
   for (auto& e : t->evpool) cudaEventDestroy(e);
   for (auto& e : t->io_events) cudaEventDestroy(e);
@@ -734,14 +735,15 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
         if (ccost[c] > 1.5 * target) nsplit = std::min(nc, (int)std::lround(ccost[c] / target));
         else tpc = std::max(1, std::min(nt, (int)(target / ccost[c])));
         tpc = (nt + ((nt + tpc - 1) / tpc) - 1) / ((nt + tpc - 1) / tpc);   // even task ranges
+        tpc = std::min(nt, (tpc + nteam - 1) / nteam * nteam);              // whole tasks per team: a multiple of the team count
         for (int k = 0; k < nsplit; ++k) {
           GramDesc d;
           d.tg = c;
-          d.nteam = nteam;
+          d.nteam = 1;                                                      // a team owns whole tasks: one partial per (task, descriptor)
           d.gbegin = G.cls_begin[c] + (int)((long long)nc * k / nsplit);
           d.gend = G.cls_begin[c] + (int)((long long)nc * (k + 1) / nsplit);
           d.hoff = P.hstride;
-          P.hstride += (long long)nteam * 4 * (c == 0 ? 16 : 64 * c * c);   // GramCfg<c>::ND squared per block
+          P.hstride += (long long)4 * (c == 0 ? 16 : 64 * c * c);           // GramCfg<c>::ND squared per block
           const int di = (int)all_desc.size() - P.desc0;
           all_desc.push_back(d);
           for (int t0 = 0; t0 < nt; t0 += tpc) {
@@ -929,8 +931,18 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
       if ((rc = ev_mark(t, 5))) return rc;
       k_task_prep<<<(nt + 127) / 128, 128, 0, st>>>(nt, SA.mz, SA.mrel, const_cast<double2*>(SA.mzinv), const_cast<double2*>(SA.mrinv));
       GM_LAUNCH_CHECK(h);
-      k_small<<<dim3((nt + GM_SMALL_WARPS - 1) / GM_SMALL_WARPS, SA.nseg), GM_SMALL_WARPS * 32, 0, st>>>(SA);
-      GM_LAUNCH_CHECK(h);
+      int nseg0 = 0;                                 // segments are listed class 0 first
+      for (const SmallSeg& sgm : small_segs) nseg0 += sgm.cls == 0 ? 1 : 0;
+      const int gx = (nt + GM_SMALL_WARPS - 1) / GM_SMALL_WARPS;
+      if (nseg0 > 0) {
+        k_small<4, GM_SMALL_MINB4><<<dim3(gx, nseg0), GM_SMALL_WARPS * 32, 0, st>>>(SA);
+        GM_LAUNCH_CHECK(h);
+      }
+      if (SA.nseg > nseg0) {
+        SA.segs += nseg0;
+        k_small<8, GM_SMALL_MINB8><<<dim3(gx, SA.nseg - nseg0), GM_SMALL_WARPS * 32, 0, st>>>(SA);
+        GM_LAUNCH_CHECK(h);
+      }
       if ((rc = ev_mark(t, 5))) return rc;
     }
 
@@ -1043,8 +1055,9 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
         GM_CUDA_TRY(cudaStreamWaitEvent(t->d2h_stream, t->io_events[nbatch + bi], 0));
         GM_CUDA_TRY(cudaMemcpyAsync(hio->out_scal + (size_t)t0 * nmode * GM_NSCAL, d_out_scal + (size_t)t0 * nmode * GM_NSCAL,
                                     sizeof(double) * (size_t)nt * nmode * GM_NSCAL, cudaMemcpyDeviceToHost, t->d2h_stream));
-        GM_CUDA_TRY(cudaMemcpyAsync(hio->out_phase + (size_t)t0 * 4 * t->nang, d_out_phase + (size_t)t0 * 4 * t->nang,
-                                    sizeof(double) * (size_t)nt * 4 * t->nang, cudaMemcpyDeviceToHost, t->d2h_stream));
+        if (hio->out_phase)
+          GM_CUDA_TRY(cudaMemcpyAsync(hio->out_phase + (size_t)t0 * 4 * t->nang, d_out_phase + (size_t)t0 * 4 * t->nang,
+                                      sizeof(double) * (size_t)nt * 4 * t->nang, cudaMemcpyDeviceToHost, t->d2h_stream));
         if (t->gsf_ng > 0 && t->gsf_coef_host) {
           GM_CUDA_TRY(cudaMemcpyAsync(t->gsf_coef_host + (size_t)t0 * 6 * t->gsf_ng, t->gsf_coef.as<double>() + (size_t)t0 * 6 * t->gsf_ng,
                                       sizeof(double) * (size_t)nt * 6 * t->gsf_ng, cudaMemcpyDeviceToHost, t->d2h_stream));
@@ -1068,6 +1081,12 @@ static int fetch_stats(gm_table_t t) {
   GM_CUDA_TRY(cudaMemcpyAsync(s, t->stats.p, sizeof(s), cudaMemcpyDeviceToHost, t->h->stream));
   GM_CUDA_TRY(cudaStreamSynchronize(t->h->stream));
   for (int i = 0; i < 4; ++i) t->last_stats[i] = (double)s[i];
+  t->last_stats[5] = (double)s[5];
+  if (s[5] != 0) {
+    // sqrt(w_phase) is folded into the coefficients: a negative phase weight has no meaning there (the outputs hold NaN)
+    gm_set_error("invalid argument: %llu negative w_phase value(s); split signed weights into w+ and w- (sums are linear in w)", s[5]);
+    return GM_EINVAL;
+  }
   return GM_OK;
 }
 
@@ -1085,7 +1104,7 @@ extern "C" int gm_table_run(gm_table_t t, int ntask, const double* mz, const dou
                             const double* w_scal, int flags, double* out_scal, double* out_phase) {
   GM_REQUIRE(t != nullptr, "table is NULL");
   GM_REQUIRE(ntask > 0 && nmode >= 1 && nmode <= 32, "ntask / nmode out of range");
-  GM_REQUIRE(mz && mrel && w_phase && out_scal && out_phase, "NULL argument");
+  GM_REQUIRE(mz && mrel && w_phase && out_scal && (out_phase || (flags & GM_F_PHASE_ON_DEVICE)), "NULL argument");
   GM_REQUIRE(w_scal || nmode == 1, "w_scal is required when nmode > 1");
   gm_handle_t h = t->h;
   GM_CUDA_TRY(cudaSetDevice(h->device));
@@ -1099,7 +1118,7 @@ extern "C" int gm_table_run(gm_table_t t, int ntask, const double* mz, const dou
   if (w_scal && (rc = t->h->scratch_wscal.ensure(sizeof(double) * nw * nmode))) return rc;
   GM_CUDA_TRY(cudaMemcpyAsync(t->mz.p, mz, sizeof(double2) * ntask, cudaMemcpyHostToDevice, st));
   GM_CUDA_TRY(cudaMemcpyAsync(t->mrel.p, mrel, sizeof(double2) * ntask, cudaMemcpyHostToDevice, st));
-  HostIO hio = {w_phase, w_scal, out_scal, out_phase};
+  HostIO hio = {w_phase, w_scal, out_scal, (flags & GM_F_PHASE_ON_DEVICE) ? nullptr : out_phase};
   rc = table_run_core(t, ntask, t->mz.as<double>(), t->mrel.as<double>(), nmode, t->h->scratch_wphase.as<double>(),
                       w_scal ? t->h->scratch_wscal.as<double>() : nullptr, flags, t->out_scal.as<double>(), t->out_phase.as<double>(), nullptr,
                       nullptr, false, &hio);
@@ -1195,7 +1214,7 @@ extern "C" int gm_table_run_psd(gm_table_t t, int ntask, const double* mz, const
                                 const double* psd_params, const double* frac, int flags, double* out_scal, double* out_phase) {
   GM_REQUIRE(t != nullptr, "table is NULL");
   GM_REQUIRE(ntask > 0 && nmode >= 1 && nmode <= 32, "ntask / nmode out of range");
-  GM_REQUIRE(mz && mrel && psd_params && frac && out_scal && out_phase, "NULL argument");
+  GM_REQUIRE(mz && mrel && psd_params && frac && out_scal && (out_phase || (flags & GM_F_PHASE_ON_DEVICE)), "NULL argument");
   GM_REQUIRE(psd_kind >= GM_PSD_LOGNORM && psd_kind <= GM_PSD_DU, "unknown psd_kind");
   GM_REQUIRE(psd_kind != GM_PSD_LOGNORM || t->have_dr, "GM_PSD_LOGNORM needs gm_table_set_dr first");
   GM_REQUIRE(t->nx >= 2, "need at least two grid points");
@@ -1221,7 +1240,7 @@ extern "C" int gm_table_run_psd(gm_table_t t, int ntask, const double* mz, const
                                t->psd_frac.as<double>(), t->h->scratch_wscal.as<double>(), t->h->scratch_wphase.as<double>(), separate ? 1 : 0);
   GM_LAUNCH_CHECK(h);
   t->psd_separate = separate;
-  HostIO hio = {nullptr, nullptr, out_scal, out_phase};   // results are downloaded batch by batch behind the kernels
+  HostIO hio = {nullptr, nullptr, out_scal, (flags & GM_F_PHASE_ON_DEVICE) ? nullptr : out_phase};   // results are downloaded batch by batch behind the kernels
   rc = table_run_core(t, ntask, t->mz.as<double>(), t->mrel.as<double>(), nmode, t->h->scratch_wphase.as<double>(),
                       separate ? t->h->scratch_wscal.as<double>() : nullptr, flags, t->out_scal.as<double>(), t->out_phase.as<double>(), nullptr,
                       nullptr, false, &hio);
@@ -1244,6 +1263,30 @@ extern "C" int gm_table_device_outputs(gm_table_t t, double** out_scal, double**
   GM_REQUIRE(t != nullptr, "table is NULL");
   if (out_scal) *out_scal = t->out_scal.as<double>();
   if (out_phase) *out_phase = t->out_phase.as<double>();
+  return GM_OK;
+}
+
+extern "C" int gm_table_fetch_normalized(gm_table_t t, int ntask, const double* theta_rad, const double* sin_theta, double* p11, double* p12,
+                                         double* p33, double* p34, double* pback4) {
+  GM_REQUIRE(t && theta_rad && sin_theta && p11 && p12 && p33 && p34 && pback4, "NULL argument");
+  GM_REQUIRE(ntask > 0 && t->out_phase.p && t->out_phase.cap >= sizeof(double) * (size_t)ntask * 4 * t->nang, "no phase sums of that many tasks on the device");
+  gm_handle_t h = t->h;
+  GM_CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  int rc;
+  const size_t plane = (size_t)ntask * t->nang;
+  if ((rc = t->norm_planes.ensure(sizeof(double) * (4 * plane + 4 * (size_t)ntask))) || (rc = t->norm_ang.ensure(sizeof(double) * 2 * t->nang))) return rc;
+  double* d_ang = t->norm_ang.as<double>();
+  GM_CUDA_TRY(cudaMemcpyAsync(d_ang, theta_rad, sizeof(double) * t->nang, cudaMemcpyHostToDevice, st));
+  GM_CUDA_TRY(cudaMemcpyAsync(d_ang + t->nang, sin_theta, sizeof(double) * t->nang, cudaMemcpyHostToDevice, st));
+  double* d_pl = t->norm_planes.as<double>();
+  k_phase_norm<<<ntask, GM_NANG_PAD, 0, st>>>(ntask, t->nang, t->out_phase.as<double>(), d_ang, d_ang + t->nang, d_pl, d_pl + 4 * plane);
+  GM_LAUNCH_CHECK(h);
+  double* dst[4] = {p11, p12, p33, p34};
+  for (int q = 0; q < 4; ++q)
+    GM_CUDA_TRY(cudaMemcpyAsync(dst[q], d_pl + (size_t)q * plane, sizeof(double) * plane, cudaMemcpyDeviceToHost, st));
+  GM_CUDA_TRY(cudaMemcpyAsync(pback4, d_pl + 4 * plane, sizeof(double) * 4 * (size_t)ntask, cudaMemcpyDeviceToHost, st));
+  GM_CUDA_TRY(cudaStreamSynchronize(st));
   return GM_OK;
 }
 

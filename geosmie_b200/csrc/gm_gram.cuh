@@ -73,8 +73,8 @@ struct GramCfg {
   static_assert(R <= GM_GRAM_MAX_SLOTS && R * SLOT_DBL <= GM_GRAM_RING_DBL, "ring does not fit");
 };
 
-// Ring protocol.  Team t owns the DEPTH slots [t DEPTH, (t + 1) DEPTH); lane t of the producer warp feeds them (the lanes run
-// independently, so a slow team never blocks the others).  tags[slot] = number of coefficient rows copied into the slot
+// Ring protocol.  Team t owns the DEPTH slots [t DEPTH, (t + 1) DEPTH) and whole TASKS of the work item (t0 + t, t0 + t + NTEAM, ...);
+// lane t of the producer warp feeds them (the lanes run independently, so a slow team never blocks the others).  tags[slot] = number of coefficient rows copied into the slot
 // (rows beyond are treated as zero by the consumers, nothing is copied for them), 0 = end-of-task marker.
 template <int TG>
 __device__ __forceinline__ void gram_cta(const GramArgs& A, const GramItem it, const GramDesc d, double* ring, uint64_t* full,
@@ -96,43 +96,29 @@ __device__ __forceinline__ void gram_cta(const GramArgs& A, const GramItem it, c
 
   if (warp == GM_CONTRACT_WARPS) {
     // ------------------------------------------------------------------------------------------ producer warp
-    int m = 0;        // slots produced so far by this lane (for team `lane`)
-    int nbase = 0;    // active groups handed out so far: group number n goes to team n % NTEAM
-    auto acquire = [&]() -> int {
-      const int s = lane * DEPTH + m % DEPTH;
-      if (m >= DEPTH) mbar_wait(&empty[s], ((m / DEPTH) - 1) & 1);
-      ++m;
-      return s;
-    };
-    for (int task = it.t0; task < it.t1; ++task) {
-      const unsigned char* ga = A.gact + (size_t)task * A.ngroup;
-      const double* coef_t = A.coef + (size_t)task * A.task_stride;
-      for (int c0 = d.gbegin; c0 < d.gend; c0 += 32) {
-        const int idx = c0 + lane;
-        const int g = idx < d.gend ? A.glist[idx] : -1;
-        const bool active = g >= 0 && ga[g] != 0;
-        const unsigned mask = __ballot_sync(0xffffffffu, active);
-        if (active) {
-          const int rank = __popc(mask & ((1u << lane) - 1u));
-          cand[rank] = A.grow[g];
-          cand[32 + rank] = GM_KSTEP * A.gk4[g];
+    // Team t works through the tasks it.t0 + t, it.t0 + t + NTEAM, ... of the work item, each with ALL groups of the descriptor:
+    // one partial H per (task, descriptor) instead of one per team, and NTEAM times fewer end-of-task flushes (with 2..12 groups per
+    // task and class, as on optics_SU, the flushes of the round-robin group deal cost as much as the DMMAs).  Lane t of this warp
+    // feeds team t; the lanes run independently.
+    if (lane < NTEAM) {
+      int m = 0;      // slots produced so far by this lane
+      for (int task = it.t0 + lane; task < it.t1; task += NTEAM) {
+        const unsigned char* ga = A.gact + (size_t)task * A.ngroup;
+        const double* coef_t = A.coef + (size_t)task * A.task_stride;
+        for (int idx = d.gbegin; idx < d.gend; ++idx) {
+          const int g = A.glist[idx];
+          if (ga[g] == 0) continue;
+          const int row = A.grow[g], nr = GM_KSTEP * A.gk4[g];
+          const int s = lane * DEPTH + m % DEPTH;
+          if (m >= DEPTH) mbar_wait(&empty[s], ((m / DEPTH) - 1) & 1);
+          ++m;
+          tags[s] = nr;
+          mbar_expect_tx(&full[s], (uint32_t)(nr * GM_SB * 8));
+          bulk_g2s(ring + (size_t)s * SLOT_DBL, coef_t + (size_t)row * GM_SB, (uint32_t)(nr * GM_SB * 8), &full[s]);
         }
-        __syncwarp();
-        const int cnt = __popc(mask);
-        if (lane < NTEAM) {
-          for (int k = (lane + NTEAM - nbase % NTEAM) % NTEAM; k < cnt; k += NTEAM) {
-            const int row = cand[k], nr = cand[32 + k];
-            const int s = acquire();
-            tags[s] = nr;
-            mbar_expect_tx(&full[s], (uint32_t)(nr * GM_SB * 8));
-            bulk_g2s(ring + (size_t)s * SLOT_DBL, coef_t + (size_t)row * GM_SB, (uint32_t)(nr * GM_SB * 8), &full[s]);
-          }
-        }
-        nbase += cnt;
-        __syncwarp();
-      }
-      if (lane < NTEAM) {   // end-of-task marker of this team
-        const int s = acquire();
+        const int s = lane * DEPTH + m % DEPTH;       // end-of-task marker
+        if (m >= DEPTH) mbar_wait(&empty[s], ((m / DEPTH) - 1) & 1);
+        ++m;
         tags[s] = 0;
         mbar_arrive(&full[s]);
       }
@@ -164,7 +150,8 @@ __device__ __forceinline__ void gram_cta(const GramArgs& A, const GramItem it, c
 #pragma unroll
       for (int j = 0; j < NJ; ++j) acc[q][i][j][0] = acc[q][i][j][1] = 0.0;
 
-  int task = it.t0;
+  int task = it.t0 + team;
+  if (task >= it.t1) return;                      // fewer tasks than teams in this work item
   for (int m = 0;; ++m) {
     const int s = team * DEPTH + m % DEPTH;
     mbar_wait(&full[s], (m / DEPTH) & 1);
@@ -237,7 +224,7 @@ __device__ __forceinline__ void gram_cta(const GramArgs& A, const GramItem it, c
       }
     } else {
       // end of task: this team's partial H -> global (fixed slot: summed in fixed order by k_gram_sum), then reset
-      double* hp = A.hpart + (size_t)task * A.hstride + d.hoff + (size_t)team * 4 * N * N;
+      double* hp = A.hpart + (size_t)task * A.hstride + d.hoff;     // the only partial of this (task, descriptor)
       if constexpr (TG == 0) {
         // 4 x 4 blocks: lane (lr, lk) holds rows lr, columns 2 lk, 2 lk + 1 of the two 8 x 8 products
         const int r4 = lr & 3, c4 = 2 * (lk & 1);
@@ -266,11 +253,11 @@ __device__ __forceinline__ void gram_cta(const GramArgs& A, const GramItem it, c
             acc[q][i][j][0] = acc[q][i][j][1] = 0.0;
           }
       }
-      ++task;
+      task += NTEAM;
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
-    if (nr == 0 && task == it.t1) break;
+    if (nr == 0 && task >= it.t1) break;
   }
 }
 

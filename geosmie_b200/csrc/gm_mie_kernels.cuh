@@ -187,6 +187,9 @@ struct CoeffArgs {
 #ifndef GM_COEFF_SHORT_START
 #define GM_COEFF_SHORT_START 0
 #endif
+#ifndef GM_COEF_STCS
+#define GM_COEF_STCS 0
+#endif
 #if GM_COEFF_TPC == 1
 #define GM_COEFF_TASK_LOOP const int task = blockIdx.y;
 #define GM_COEFF_NEXT_TASK return
@@ -223,6 +226,10 @@ __global__ void __launch_bounds__(128, GM_COEFF_MINB) k_coeff(CoeffArgs A) {
       for (int k = 0; k < A.nmode; ++k) any |= valid && A.wscal[((size_t)task * A.nmode + k) * A.nx + i] != 0.0;
   }
   const bool act = valid && (MODE == 1 || A.dense || any);
+  if (TABLE && A.stats && A.scale_sqrtw) {
+    const unsigned nneg = __popc(__ballot_sync(0xffffffffu, wp < 0.0));
+    if (nneg && lane == 0) atomicAdd(&A.stats[5], (unsigned long long)nneg);     // reported as GM_EINVAL by the host-buffer calls
+  }
   const double2 z = make_double2(mzv.x * xi, mzv.y * xi);                     // mie_coeffs.py:96
 #if GM_COEFF_SHORT_START
   // experiment (default off): start the downward recurrence 4 + ceil(2.5 |z|) orders (at most the reference's 16) above
@@ -347,8 +354,10 @@ __global__ void __launch_bounds__(128, GM_COEFF_MINB) k_coeff(CoeffArgs A) {
       b_next = bn;
       if (TABLE) {
         const double f = c2n * sw;
-        cp = make_double2((an.x + bn.x) * f, (an.y + bn.y) * f);
-        cm = make_double2((an.x - bn.x) * f, (an.y - bn.y) * f);
+        if (sw != 0.0) {   // a zero-weight particle of a dense run adds exact zeros even where its coefficients are not finite
+          cp = make_double2((an.x + bn.x) * f, (an.y + bn.y) * f);
+          cm = make_double2((an.x - bn.x) * f, (an.y - bn.y) * f);
+        }
       } else {
         A.ab[abo + n - 1] = make_double4(an.x, an.y, bn.x, bn.y);
       }
@@ -356,8 +365,13 @@ __global__ void __launch_bounds__(128, GM_COEFF_MINB) k_coeff(CoeffArgs A) {
 #ifndef GM_COEFF_NOSTORE   // (diagnostic builds only: the kernel without its coefficient-stream stores)
     if (TABLE) {
       double* r = crow + (size_t)(n - 1) * GM_SB;
+#if GM_COEF_STCS   // streaming (evict-first) stores: the stream is written once and read once, several L2 capacities later
+      __stcs(reinterpret_cast<double2*>(r), cp);
+      __stcs(reinterpret_cast<double2*>(r + 64), cm);
+#else
       *reinterpret_cast<double2*>(r) = cp;
       *reinterpret_cast<double2*>(r + 64) = cm;
+#endif
     }
 #endif
   }
@@ -403,7 +417,7 @@ __global__ void __launch_bounds__(128, GM_COEFF_MINB) k_coeff(CoeffArgs A) {
       double v[16];
 #pragma unroll
       for (int s = GM_NSCAL; s < 16; ++s) v[s] = 0.0;
-      const bool on = act && (A.dense || w != 0.0);
+      const bool on = act && w != 0.0;   // w == 0 adds exact zeros (also where a dense run met a non-finite efficiency)
       const double x2w = x2 * w, x4w = x4 * w;
       v[GM_S_W] = valid ? w : 0.0;
       v[GM_S_X2W] = valid ? x2w : 0.0;
@@ -776,4 +790,47 @@ __global__ void __launch_bounds__(128) k_props_nat(int n, const double* __restri
   o[3] = (qbr * qbr + qbi * qbi) / y2;
   o[4] = 4.0 / y2 * sasy / o[1];
   o[5] = o[3] / o[1];
+}
+
+// ================================================================================================ k_phase_norm
+// grid = ntask, block = GM_NANG_PAD.  dointegration.py:977-988 on the raw phase sums [task][4][nang] -> planes [4][ntask][nang] and
+// pback4 [task][4].  The trapezoid terms d_i (y_i + y_{i+1}) / 2 are summed per warp by a fixed shuffle tree, then in warp order.
+__global__ void __launch_bounds__(GM_NANG_PAD) k_phase_norm(int ntask, int nang, const double* __restrict__ phase, const double* __restrict__ theta,
+                                                           const double* __restrict__ sint, double* __restrict__ planes, double* __restrict__ pback4) {
+  __shared__ double y[GM_NANG_PAD];
+  __shared__ double wsum[GM_NANG_PAD / 32];
+  __shared__ double total;
+  const int task = blockIdx.x, a = threadIdx.x;
+  const double* P = phase + (size_t)task * 4 * nang;
+  double p[4] = {0, 0, 0, 0};
+  if (a < nang) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) p[q] = P[(size_t)q * nang + a];
+    y[a] = p[0] * sint[a];
+  }
+  __syncthreads();
+  double term = 0.0;
+  if (a + 1 < nang) term = (theta[a + 1] - theta[a]) * (y[a + 1] + y[a]) / 2.0;
+  term = warp_sum(term);
+  if ((a & 31) == 0) wsum[a >> 5] = term;
+  __syncthreads();
+  if (a == 0) {
+    double s = 0.0;
+    for (int w = 0; w < GM_NANG_PAD / 32; ++w) s += wsum[w];
+    total = s;
+  }
+  __syncthreads();
+  if (a < nang) {
+    const double p11n = 2.0 * p[0] / total;
+    double o[4];
+    o[0] = p11n;
+#pragma unroll
+    for (int q = 1; q < 4; ++q) o[q] = p[q] * p11n / p[0];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) planes[((size_t)q * ntask + task) * nang + a] = o[q];
+    if (a == nang - 1) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) pback4[(size_t)task * 4 + q] = o[q];
+    }
+  }
 }

@@ -21,11 +21,16 @@
 #pragma once
 #include "gm_gram.cuh"
 
-#ifndef GM_SMALL_MINB
-#define GM_SMALL_MINB 3          // CTAs of 128 threads per SM (register budget 65536 / (128 * MINB))
+#ifndef GM_SMALL_MINB4
+#define GM_SMALL_MINB4 4         // CTAs of 128 threads per SM of the 4-order / 8-order instantiation (register budget 65536 / (128 * MINB))
+#define GM_SMALL_MINB8 3
 #endif
 #ifndef GM_SMALL_SHORT_START
-#define GM_SMALL_SHORT_START 0   // 1: start the D_n recurrence 4 + ceil(2.5 |z|) (<= 16) orders above max(nmax, |z|) instead of 16
+// 1: the D_n recurrence starts 4 + ceil(2.5 |z|) (at most the reference's 16) orders above max(nmax, |z|).  Starting from D = 0, the
+// error of D_n falls by ~ |z|^2 / (4 j^2) per order j: for these groups (nmax <= 8, |z| <~ 5) D_n is converged to <= 1e-14 where the
+// reference's fixed 16 orders (mie_coeffs.py:101) are; CPU error study in profiles/r01k_coeff_start_offset_study.txt, GPU parity
+// of the complete optics_SU / optics_BC tables unchanged.  0 = exactly the reference's start order.
+#define GM_SMALL_SHORT_START 1
 #endif
 constexpr int GM_SMALL_WARPS = 4;
 constexpr int GM_SMALL_MAXSEG = 12;   // k_gram_sum adds up to 12 partial blocks per descriptor
@@ -87,7 +92,7 @@ __device__ __forceinline__ void small_item(const SmallArgs& A, const SmallSeg sg
   double acc[STACK ? 2 : 4][2];
 #pragma unroll
   for (int q = 0; q < (STACK ? 2 : 4); ++q) acc[q][0] = acc[q][1] = 0.0;
-  unsigned st_ev = 0, st_nm = 0, st_nx = 0, st_k4 = 0;
+  unsigned st_ev = 0, st_nm = 0, st_nx = 0, st_k4 = 0, st_neg = 0;
 
   const double sgn = (lk & 1) ? -1.0 : 1.0;
   const int lane_off = STACK ? (lr & 3) * GM_SB + (lr >> 2) * 64 + lk : lr * GM_SB + lk;
@@ -101,6 +106,7 @@ __device__ __forceinline__ void small_item(const SmallArgs& A, const SmallSeg sg
     const double wp = valid ? wp_t[i] : 0.0;
     const double ws = valid ? (ws_t ? ws_t[i] : wp) : 0.0;
     const bool act = valid && (A.dense || wp != 0.0 || ws != 0.0);
+    st_neg += (valid && wp < 0.0) ? 1u : 0u;
     if (!__any_sync(0xffffffffu, act)) continue;   // the group adds exact zeros to every sum (x-moment sums included: w == 0)
     const double xinv = valid ? A.xinv[i] : 1.0;
     // Riccati-Bessel values of orders 0..ROWS, requested before the recurrence starts (their latency hides behind phase 1)
@@ -138,8 +144,8 @@ __device__ __forceinline__ void small_item(const SmallArgs& A, const SmallSeg sg
       tt.x = on ? fma(f2, zinv.x, -ti.x) : tt.x;
       tt.y = on ? fma(f2, zinv.y, -ti.y) : tt.y;
     }
-    // ---- phase 2: orders ROWS..1, unrolled and branch-free.  Every active lane has nmx >= nm + 4 > ROWS >= n here... unless
-    // J - 1 < ROWS, which cannot happen for an active group (nmx >= 2 + 4); lanes that are not active compute discarded values.
+    // ---- phase 2: orders ROWS..1, unrolled and branch-free.  A lane joins the recurrence at its own order nmx - 1 (`on`), which may
+    // lie inside this range when its nmax is far below the group's (unsorted grids); lanes that are not active compute discarded values.
     double sext = 0.0, ssca = 0.0, qbr = 0.0, qbi = 0.0, sasy = 0.0;
     double2 a_next = make_double2(0.0, 0.0), b_next = make_double2(0.0, 0.0);
 #pragma unroll
@@ -151,6 +157,7 @@ __device__ __forceinline__ void small_item(const SmallArgs& A, const SmallSeg sg
       tt.x = on ? fma(fr2, zinv.x, -ti.x) : tt.x;
       tt.y = on ? fma(fr2, zinv.y, -ti.y) : tt.y;
       const bool emit = act && r <= nm;
+      const bool wnz = sw != 0.0;   // a zero-weight particle of a dense run adds exact zeros even where a_n, b_n are not finite
       const double nox = (double)r * xinv;
       double2 da = cmul(D, minv);                                               // mie_coeffs.py:124
       da.x += nox;
@@ -178,8 +185,8 @@ __device__ __forceinline__ void small_item(const SmallArgs& A, const SmallSeg sg
       b_next = bn;
       const double f = nt.x * sw;
       double* row = tile + (r - 1) * GM_SB + 2 * lane;
-      *reinterpret_cast<double2*>(row) = make_double2((an.x + bn.x) * f, (an.y + bn.y) * f);
-      *reinterpret_cast<double2*>(row + 64) = make_double2((an.x - bn.x) * f, (an.y - bn.y) * f);
+      *reinterpret_cast<double2*>(row) = make_double2(wnz ? (an.x + bn.x) * f : 0.0, wnz ? (an.y + bn.y) * f : 0.0);
+      *reinterpret_cast<double2*>(row + 64) = make_double2(wnz ? (an.x - bn.x) * f : 0.0, wnz ? (an.y - bn.y) * f : 0.0);
     }
     // ---- per-particle efficiencies (mie_props.py:44-68) and this lane's share of the size-distribution sums
     {
@@ -188,7 +195,7 @@ __device__ __forceinline__ void small_item(const SmallArgs& A, const SmallSeg sg
       const double qb = act ? (qbr * qbr + qbi * qbi) * iy2 : 0.0, gq = act ? 4.0 * iy2 * sasy : 0.0;
       const double x2 = xi * xi, x3 = x2 * xi, x4 = x2 * x2;
       const double w = valid ? ws : 0.0;
-      const bool on = act && (A.dense || w != 0.0);
+      const bool on = act && w != 0.0;
       const double x2w = x2 * w, x4w = x4 * w;
       S[GM_S_W] += w;
       S[GM_S_X2W] += valid ? x2w : 0.0;
@@ -259,8 +266,9 @@ __device__ __forceinline__ void small_item(const SmallArgs& A, const SmallSeg sg
   }
   if (A.stats) {
     const unsigned ne = __reduce_add_sync(0xffffffffu, st_ev), snm = __reduce_add_sync(0xffffffffu, st_nm),
-                   snx = __reduce_add_sync(0xffffffffu, st_nx);
+                   snx = __reduce_add_sync(0xffffffffu, st_nx), sneg = __reduce_add_sync(0xffffffffu, st_neg);
     if (lane == 0) {
+      if (sneg) atomicAdd(&A.stats[5], (unsigned long long)sneg);
       atomicAdd(&A.stats[0], (unsigned long long)ne);
       atomicAdd(&A.stats[1], (unsigned long long)snm);
       atomicAdd(&A.stats[2], (unsigned long long)snx);
@@ -269,16 +277,14 @@ __device__ __forceinline__ void small_item(const SmallArgs& A, const SmallSeg sg
   }
 }
 
-// grid = (ceil(ntask / 4), nseg), block = 128: the four warps of a CTA take four consecutive tasks of the same segment, so that the
-// Bessel rows, x, 1/x and nmax of its groups are shared through L1.
-__global__ void __launch_bounds__(GM_SMALL_WARPS * 32, GM_SMALL_MINB) k_small(SmallArgs A) {
-  __shared__ __align__(16) double tiles[GM_SMALL_WARPS][8 * GM_SB];
+// grid = (ceil(ntask / 4), segments of the class), block = 128: the four warps of a CTA take four consecutive tasks of the same
+// segment, so that the Bessel rows, x, 1/x and nmax of its groups are shared through L1.  One instantiation per class: the 4-order
+// body fits 128 registers (16 warps per SM), the 8-order body needs 168 (12 warps per SM; at 128 it spills 300 B).
+template <int ROWS, int MINB>
+__global__ void __launch_bounds__(GM_SMALL_WARPS * 32, MINB) k_small(SmallArgs A) {
+  __shared__ __align__(16) double tiles[GM_SMALL_WARPS][ROWS * GM_SB];
   const int warp = threadIdx.x >> 5;
   const int task = blockIdx.x * GM_SMALL_WARPS + warp;
   if (task >= A.ntask) return;
-  const SmallSeg sg = A.segs[blockIdx.y];
-  if (sg.cls == 0)
-    small_item<4>(A, sg, task, tiles[warp]);
-  else
-    small_item<8>(A, sg, task, tiles[warp]);
+  small_item<ROWS>(A, A.segs[blockIdx.y], task, tiles[warp]);
 }

@@ -220,6 +220,8 @@ def combine_modes(scal, phase, fracs, lam, reff0, rhop0, rhop):
     t['bbck'] = 3. / 4. * t['qb'] * conv / (4 * np.pi)
     ret = {k: np.sum(fr * v, axis=-1) for k, v in t.items()}       # ret[key] += frac * thisret[key], :1199-1200
     ret['lidar_ratio'] = np.zeros(lead)
+    if phase is None:          # the phase matrix stays on the device (gm_table_fetch_normalized delivers it normalised)
+        return ret
     ph = np.asarray(phase, dtype=float)
     ret['p11'] = ph[..., 0, :]
     ret['p12'] = ph[..., 1, :]
@@ -443,6 +445,10 @@ class BinPlan(object):
 
     def __init__(self, params, radind, lambarr, rh_used, part_m, water_m, cells=None, device_psd=False):
         self.radind = radind
+        if device_psd and float(np.asarray(rh_used)[0]) != 0.0:
+            # reff_mass0 is defined at the humidity VALUE 0.0 (calculatePSD(..., onerh=0., ...), dointegration.py:837-838); the
+            # device-PSD path takes it from the RH-index-0 cell, which is the same thing only when the list starts at 0.0
+            device_psd = False
         if params['psd']['type'] == 'du':
             # the reference's 'du' grid, (linspace(log10 x))**10 (dointegration.py:456-460), is not monotonic, so getDR and with
             # it the number weights change sign along the grid (:640-648): build them with numpy like the reference and let
@@ -595,24 +601,17 @@ class BinPlan(object):
         return (np.sqrt(self.m.reshape(-1) ** 2 * 1.0), self.psd_par.reshape(ncell * nmode, 1, 4),
                 np.tile(fr, ncell).reshape(ncell * nmode, 1), nmode)
 
-    def evaluate(self, table, elide=True):
-        """Run every task of the bin on `table`; returns (scal, phase, tasks_per_cell)."""
+    def evaluate(self, table, elide=True, phase_on_device=False):
+        """Run every task of the bin on `table`; returns (scal, phase, tasks_per_cell).  phase_on_device=True (device-PSD path with
+        one task per cell only): the raw phase sums stay on the GPU and `phase` is None -- see Table.fetch_normalized."""
         if self.device_psd:
             mz, par, fr, tpc = self.tasks_psd()
             if self.psd_kind == _lib.PSD_LOGNORM:
                 table.set_dr(self.dr)
-            scal, phase = table.run_psd(mz, mz, self.psd_kind, par, fr, elide=elide)
+            scal, phase = table.run_psd(mz, mz, self.psd_kind, par, fr, elide=elide, phase_on_device=phase_on_device and tpc == 1)
         else:
             mz, wp, ws, tpc = self.tasks()
-            neg = wp < 0
-            if neg.any():
-                # signed number weights: sums are linear in w, so phase = phase(w+) - phase(w-); the scalar sums take the signed
-                # per-mode weights as they are
-                scal, phase = table.run(mz, mz, np.where(neg, 0.0, wp), ws, elide=elide)
-                _, phase_n = table.run(mz, mz, np.where(neg, -wp, 0.0), None, elide=True)
-                phase = phase - phase_n
-            else:
-                scal, phase = table.run(mz, mz, wp, ws, elide=elide)
+            scal, phase = table.run(mz, mz, wp, ws, elide=elide)      # signed weights ('du' grid) are split inside Table.run
         return scal, phase, tpc
 
     def reduce(self, scal, phase, tasks_per_cell):
@@ -622,7 +621,7 @@ class BinPlan(object):
             sc, ph = scal, phase
         else:
             sc = scal.reshape(ncell, tasks_per_cell, scal.shape[-1])
-            ph = phase.reshape(ncell, tasks_per_cell, 4, phase.shape[-1]).sum(axis=1)
+            ph = None if phase is None else phase.reshape(ncell, tasks_per_cell, 4, phase.shape[-1]).sum(axis=1)
         reff0 = self.reff0
         if reff0 is None:
             # reff_mass0 = sum r^4 w / sum r^3 w of the RH-index-0 weights at the same wavelength (:837-838, :1118-1121)
@@ -697,12 +696,27 @@ def fun(partID0, datatype, oppfx, oppclassic, elide=True, write=True, comm=None,
         ncell = len(plan.cells)
         li = np.array([c[0] for c in plan.cells], dtype=np.int64)
         ri = np.array([c[1] for c in plan.cells], dtype=np.int64)
-        rows = np.zeros((ncell, 2 + sum(width.values())))
+        ret, in_place = None, False
         if ncell:
             table = _lib.Table(plan.xx, plan.nmax, costarr)
-            scal, phase, tpc = plan.evaluate(table, elide=elide)
+            # One task per cell and weights made on the device (every shipped Mie species except the 'du' grid and multi-index
+            # bins): the a-posteriori normalisation runs on the GPU (k_phase_norm) and the four distinct phase-matrix planes arrive
+            # normalised -- straight in their final arrays when this rank owns the whole bin in file order (one GPU).
+            on_device = plan.device_psd and plan.nri == 1 and keep_phase
+            scal, phase, tpc = plan.evaluate(table, elide=elide, phase_on_device=on_device)
+            ret = plan.reduce(scal, phase, tpc)
+            if phase is None:
+                in_place = world == 1 and ncell == nl * nr
+                dst = [vals[k][radind].reshape(ncell, na) for k in ('p11', 'p12', 'p33', 'p34')] if in_place else None
+                planes, pb = table.fetch_normalized(ang, out=dst)
+                ret['lidar_ratio'] = ret['qext'] / ret['qb'] * 4 * np.pi
+                ret['ssa'] = ret['qsca'] / ret['qext']
+                ret['p11'], ret['p12'], ret['p33'], ret['p34'] = planes
+                ret['p22'], ret['p44'] = planes[0], planes[2]          # spheres (calculateScatVals, dointegration.py:1044-1050)
+                ret['pback'] = pb[:, [0, 1, 2, 3, 0, 2]]
+            else:
+                ret = postprocess(ret, ang)
             table.close()
-            ret = postprocess(plan.reduce(scal, phase, tpc), ang)
             # mass0 = volume(RH index 0) * rhop0 of the same (bin, lambda) (dointegration.py:992-997)
             vol0 = np.zeros(nl)
             sel0 = ri == 0
@@ -716,28 +730,40 @@ def fun(partID0, datatype, oppfx, oppclassic, elide=True, write=True, comm=None,
             ret['rUp'] = plan.rUp
             ret['refreal'] = plan.m[:, 0].real
             ret['refimag'] = -np.abs(plan.m[:, 0].imag)
-            rows[:, 0], rows[:, 1] = li, ri
-            o = 2
-            for k in keys:
-                rows[:, o:o + width[k]] = np.asarray(ret[k]).reshape(ncell, width[k])
-                o += width[k]
         if world > 1:
-            rows = comm.gather_rows(rows)          # NCCL gather over NVLink (gloo on CPU)
+            # only the distinct columns travel: p22 / p44 are rebuilt from p11 / p33 on rank 0 when the device normalised them
+            dup = {'p22': 'p11', 'p44': 'p33'} if (plan.device_psd and plan.nri == 1 and keep_phase) else {}     # same on every rank
+            send = [k for k in keys if k not in dup]
+            rows = np.zeros((ncell, 2 + sum(width[k] for k in send)))
+            if ncell:
+                rows[:, 0], rows[:, 1] = li, ri
+                o = 2
+                for k in send:
+                    rows[:, o:o + width[k]] = np.asarray(ret[k]).reshape(ncell, width[k])
+                    o += width[k]
+            rows = comm.gather_rows(rows)          # over NVLink (peer puts or NCCL gather); gloo on CPU
             if rank != 0:
                 continue
             li, ri = rows[:, 0].astype(np.int64), rows[:, 1].astype(np.int64)
-        o = 2
-        for key in keys:
-            col = rows[:, o:o + width[key]]
-            o += width[key]
-            if _kind_of(key) == "nl":
-                # (bin, rh) variables are overwritten at every wavelength: the last one wins (dointegration.py:1026-1027)
-                last = li == li.max()
-                vals[key][radind, ri[last]] = col[last, 0]
-            elif width[key] == 1:
-                vals[key][radind, li, ri] = col[:, 0]
-            else:
-                vals[key][radind, li, ri] = col
+            ret, o = {}, 2
+            for k in send:
+                ret[k] = rows[:, o:o + width[k]] if width[k] > 1 else rows[:, o]
+                o += width[k]
+            for k, src in dup.items():
+                ret[k] = ret[src]
+        if ret is not None:
+            for key in keys:
+                col = np.asarray(ret[key])
+                if _kind_of(key) == "nl":
+                    # (bin, rh) variables are overwritten at every wavelength: the last one wins (dointegration.py:1026-1027)
+                    last = li == li.max()
+                    vals[key][radind, ri[last]] = col[last]
+                elif in_place and key in ('p11', 'p12', 'p33', 'p34'):
+                    continue                                   # written by the device-to-host copy itself
+                elif in_place:
+                    vals[key][radind] = col.reshape(vals[key][radind].shape)      # cells are in (wavelength, rh) order
+                else:
+                    vals[key][radind, li, ri] = col
         if trivial:
             # copyDryValues (dointegration.py:465-491)
             for key in vals:

@@ -17,6 +17,8 @@ def _convert_var(name, data, dims, radius_name):
     if radius_name not in dims:
         return np.array(data)
     ax = dims.index(radius_name)
+    if data.shape[ax] == 2:
+        return np.array(data)                                # shape unchanged: copied through as it is (hydrophobic.py:58, :121-122)
     if data.ndim == 1:
         return np.array([1, 2], dtype=data.dtype)            # the 1-indexed bin coordinate (:61-63)
     src = np.take(data, 0, axis=ax)                         # only bin 0 of the input is used, as in the reference

@@ -17,11 +17,19 @@ def mie_S12(coeffs, u):
     return (complex(s[0], s[1]), complex(s[2], s[3]))
 
 def mie_S12_pt(coeffs, pin, tin):
-    """S1,S2 from caller-supplied pre-multiplied pi_n/tau_n arrays (mie_props.py:112-113, :133-150).
-    pin[1]/pin[0] = (5/6)(3u)/(3/2) recovers u; the sums themselves run on the GPU."""
+    """S1,S2 from caller-supplied pre-multiplied pi_n/tau_n arrays (mie_props.py:112-113, mie_S12_backend_pt :133-150):
+    S1 = sum a_n pin_n + sum b_n tin_n, S2 = sum a_n tin_n + sum b_n pin_n over the first nmax entries.  The coefficients
+    come from the GPU (gm_mie_eval); the four nmax-long dot products with the CALLER's arrays are formed here in the
+    reference's order, so arbitrary (truncated, rescaled) pin / tin behave exactly as in the reference."""
     pin = np.asarray(pin, dtype=float)
-    u = float(pin[1] / pin[0] * 1.5 / (5.0 / 6.0) / 3.0) if len(pin) > 1 else float(np.asarray(tin)[0] / 1.5)
-    return mie_S12(coeffs, u)
+    tin = np.asarray(tin, dtype=float)
+    nmax = coeffs.nmax
+    if pin.shape[0] < nmax or tin.shape[0] < nmax:
+        raise ValueError("pin / tin must hold at least nmax = %d entries" % nmax)
+    an, bn = coeffs.an[:nmax], coeffs.bn[:nmax]
+    s1 = np.dot(an, pin[:nmax]) + np.dot(bn, tin[:nmax])
+    s2 = np.dot(an, tin[:nmax]) + np.dot(bn, pin[:nmax])
+    return (complex(s1), complex(s2))
 
 def mie_pt(u, nmax):
     """pi_n, tau_n pre-multiplied by (2n+1)/(n(n+1)) (mie_props.py:194-195, :217-231).  Host-side helper: these

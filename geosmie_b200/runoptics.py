@@ -16,6 +16,9 @@ _OPTIONS = [
     (("--name",), "name", "", "Particle file to use (default=%s)" % ""),
     (("--namelist",), "namelist", "",
      "File with list of particle files (to be passed to --file) to run iteratively. If used, overrides --file (default=%s)" % ""),
+    # the reference keeps --shape inside a string literal (runoptics.py:35-39: switched off); accepted here with its one
+    # supported value so that scripts written against older revisions keep running
+    (("--shape",), "shape", "mie", "Particle shape to use %s (default=%s)" % (['mie'], "mie")),
     (("--datatype",), "datatype", "json", "Particle data type to use %s (default=%s)" % (['json'], "json")),
     (("--dest",), "dest", ".", "Output directory to use (default=%s)" % "."),
 ]
@@ -32,6 +35,8 @@ def _parse(argv):
     for flags, dest, text in _FLAGS:
         parser.add_option(*flags, action="store_true", dest=dest, default=False, help=text)
     options, _ = parser.parse_args(argv)
+    if options.shape not in ['mie']:
+        parser.error("shape must be one of: %s (kernel-mode dust is selected by \"mode\" in the particle file)" % (['mie']))
     if options.datatype not in ['json']:
         parser.error("data type must be one of: %s" % (['json']))
     if not os.path.exists(options.dest):

@@ -59,3 +59,33 @@ def bin_plan(sp, radind=0, cells=None, fixture=DEFAULT_FIXTURE, device_psd=False
 def n_bins(sp):
     from . import dointegration as DI
     return len(DI.bins_of(SPECIES[sp])[0])
+
+
+def species_files(sp, fixture=DEFAULT_FIXTURE):
+    """Files of a run directory that reproduce a shipped species config (su / ss / bc): <sp>.json with the parameters of
+    src/config/geosparticles/<sp>.json, its refractive-index table re-written in the 'wsv' format of particleparams.py:70-77, and
+    data/refrac.water.txt (13 header lines, columns wavelength [um] n k: particleparams.py:79-82).  {relative path: text}."""
+    g = np.load(fixture)
+    ml, w = g[sp + "__mlist"], g["su__water"]
+
+    def rows(t):
+        out = []
+        for i in range(t.shape[1]):
+            um = float("%.10g" % (t[0, i] * 1e6))       # the table's own decimal value, so that um * 1e-6 is bit-exact
+            assert um * 1e-6 == t[0, i]
+            out.append("%.17g %.17g %.17g" % (um, t[1, i], t[2, i]))
+        return "\n".join(out) + "\n"
+
+    cfg = json.loads(json.dumps(SPECIES[sp]))
+    cfg["ri"] = {"format": "wsv", "path": ["ri-%s.wsv" % sp]}
+    return {sp + ".json": json.dumps(cfg), "ri-%s.wsv" % sp: rows(ml), os.path.join("data", "refrac.water.txt"): "# header\n" * 13 + rows(w)}
+
+
+def write_run_dir(d, sp, fixture=DEFAULT_FIXTURE):
+    """Write species_files(sp) below directory d (the reference's CWD-relative layout).  Returns the config file name."""
+    for name, text in species_files(sp, fixture).items():
+        path = os.path.join(d, name)
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        with open(path, "w") as fp:
+            fp.write(text)
+    return sp + ".json"

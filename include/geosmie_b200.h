@@ -43,6 +43,8 @@ extern "C" {
 #define GM_F_ELIDE_ZERO_WEIGHT 1 /* skip particles whose weights are all exactly 0 (result-neutral) */
 #define GM_F_NO_GRAM 2           /* evaluate every particle group with the per-angle contraction (k_contract); default: groups
                                     with nmax <= 64 go through the Gram-matrix form (k_gram + k_gram_eval), same sums */
+#define GM_F_PHASE_ON_DEVICE 4   /* host-buffer calls: do not download the raw phase sums (out_phase may be NULL); they stay in the
+                                    table's device buffer for gm_table_fetch_normalized / gm_gsf_expand_phase4_dev */
 
 typedef struct gm_handle_s* gm_handle_t;
 typedef struct gm_table_s* gm_table_t;
@@ -157,6 +159,14 @@ int gm_table_gsf_device(gm_table_t t, double** coef, double** cnorm);
 /* device copies of the outputs of the last host-buffer gm_table_run (valid until the next call on this table), so that
  * gm_gsf_expand_phase4_dev can be chained without a host round trip */
 int gm_table_device_outputs(gm_table_t t, double** out_scal, double** out_phase);
+/* The a-posteriori normalisation of the table driver on the device-resident phase sums of the last host-buffer gm_table_run* call
+ * of this table (replaces the numpy statements of dointegration.fun, dointegration.py:977-988, over [cells x 371] arrays):
+ *   I = trapz(p11 sin(theta), theta);  p11n = 2 p11 / I;  pXX = pXX p11n / p11 for XX = 12, 33, 34;  pback = the values at the
+ *   last angle.  theta_rad, sin_theta [nang] (host; the caller's own sin values, so the products match the reference's bits).
+ * Host outputs, each one CONTIGUOUS plane: p11, p12, p33, p34 [ntask][nang] (the caller's final arrays: p22 = p11 and p44 = p33
+ * for spheres), pback4 [ntask][4] in the order 11, 12, 33, 34.  The trapezoid sum is taken in a fixed order (deterministic). */
+int gm_table_fetch_normalized(gm_table_t t, int ntask, const double* theta_rad, const double* sin_theta, double* p11, double* p12,
+                              double* p33, double* p34, double* pback4);
 /* per-particle outputs through the table (DMMA) path: q [ntask][nx][6], s12 [ntask][nx][nang][4] (host pointers) */
 int gm_table_particles(gm_table_t t, int ntask, const double* mz, const double* mrel, double* q, double* s12);
 /* statistics of the last gm_table_run*: [0] particle evaluations, [1] sum of nmax over evaluated particles,

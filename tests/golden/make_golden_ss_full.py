@@ -155,6 +155,9 @@ def merge():
     for k in NL:
         vals["perlam__" + k] = vals["var__" + k]              # what every wavelength pass computed
         vals["var__" + k] = vals["var__" + k][:, -1, :].copy()  # what survives in the file: the last wavelength's write
+    st = _setup()
+    vals["var__wavelength"] = np.asarray(st["params"]["mList"][0][0], dtype=float)
+    vals["var__rh"] = np.asarray(st["params"]["rh"], dtype=float)          # the file's coordinate is the un-capped list
     vals["phase_cells"] = np.array(cells)
     np.savez_compressed(os.path.join(HERE, "full_ss.npz"), **vals)
     print("wrote full_ss.npz")

@@ -32,7 +32,7 @@ def _check_full_table(sp):
             assert relerr(a, r) < TOL_Q, (key, relerr(a, r))
     cells = g["phase_cells"]
     for key in ("p11", "p12", "p22", "p33", "p34", "p44"):
-        ref = g["phase__" + key]
+        ref = g["phase__" + key]                                                   # [bin, cell, ang]
         got = np.stack([vals[key][:, li, rhi, :] for li, rhi in cells], axis=1)
         scale = np.abs(g["phase__p11"]).max(axis=-1, keepdims=True)
         assert np.max(np.abs(got - ref) / scale) < TOL_P, key
@@ -48,6 +48,14 @@ def test_full_optics_bc_table():
 def test_full_optics_su_table():
     """optics_SU (BASELINE config 2): 4459 sizes x 61 wavelengths x 36 RH = 9.79 M particle evaluations."""
     _check_full_table("su")
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(GOLDEN, "full_ss.npz")), reason="full_ss.npz not generated")
+def test_full_optics_ss_table():
+    """optics_SS (BASELINE config 3), ALL 5 x 61 x 36 = 10,980 cells: every scalar variable, pback and the phase matrices of 54
+    stratified cells per bin against the unmodified reference evaluated densely on the full grids (x up to 2513, nmax up to 2567;
+    tests/golden/make_golden_ss_full.py, ~11 h of one core)."""
+    _check_full_table("ss")
 
 
 def test_optics_ss_cells():
