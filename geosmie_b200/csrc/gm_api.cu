@@ -60,6 +60,14 @@ extern "C" int gm_init(int device, gm_handle_t* out) {
   gm_handle_s* h = new gm_handle_s();
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
+  h->l2_window_max = prop.accessPolicyMaxWindowSize;
+  h->l2_persist_max = 0;
+  if (getenv("GEOSMIE_L2_PERSIST") && atoi(getenv("GEOSMIE_L2_PERSIST")) > 0 && prop.persistingL2CacheMaxSize > 0) {
+    // experiment (off by default): a slice of the 126 MB L2 set aside for the Riccati-Bessel tables (see table_run_core)
+    const size_t want = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, (size_t)atoi(getenv("GEOSMIE_L2_PERSIST")) << 20);
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) h->l2_persist_max = (long long)want;
+    else cudaGetLastError();
+  }
   // opt in to the large dynamic shared memory of the contraction kernels once
   const int smem = GM_CONTRACT_SMEM;
   GM_CUDA_TRY(cudaFuncSetAttribute(k_contract<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -210,7 +218,10 @@ struct Groups {
 };
 
 struct DevGroups {
-  DevBuf x, xinv, nmax, gboff, gk4, grow, psi, chi;
+  DevBuf x, xinv, nmax, gboff, gk4, grow, psichi;
+  double* psi_p = nullptr;
+  double* chi_p = nullptr;
+  size_t psichi_bytes = 0;
   int upload(const Groups& G, const double* hx, const int32_t* hnmax, cudaStream_t st) {
     int rc;
     if ((rc = x.ensure(sizeof(double) * G.nx))) return rc;
@@ -219,19 +230,20 @@ struct DevGroups {
     if ((rc = gboff.ensure(sizeof(long long) * G.ngroup))) return rc;
     if ((rc = gk4.ensure(sizeof(int) * G.ngroup))) return rc;
     if ((rc = grow.ensure(sizeof(int) * G.ngroup))) return rc;
-    if ((rc = psi.ensure(sizeof(double) * G.bessel_len))) return rc;
-    if ((rc = chi.ensure(sizeof(double) * G.bessel_len))) return rc;
+    if ((rc = psichi.ensure(sizeof(double) * 2 * G.bessel_len))) return rc;     // psi | chi in ONE allocation (one L2 access-policy window)
+    psi_p = psichi.as<double>();
+    chi_p = psi_p + G.bessel_len;
+    psichi_bytes = sizeof(double) * 2 * (size_t)G.bessel_len;
     GM_CUDA_TRY(cudaMemcpyAsync(x.p, hx, sizeof(double) * G.nx, cudaMemcpyHostToDevice, st));
     GM_CUDA_TRY(cudaMemcpyAsync(nmax.p, hnmax, sizeof(int) * G.nx, cudaMemcpyHostToDevice, st));
     GM_CUDA_TRY(cudaMemcpyAsync(gboff.p, G.gboff.data(), sizeof(long long) * G.ngroup, cudaMemcpyHostToDevice, st));
     GM_CUDA_TRY(cudaMemcpyAsync(gk4.p, G.gk4.data(), sizeof(int) * G.ngroup, cudaMemcpyHostToDevice, st));
     GM_CUDA_TRY(cudaMemcpyAsync(grow.p, G.grow.data(), sizeof(int) * G.ngroup, cudaMemcpyHostToDevice, st));
-    GM_CUDA_TRY(cudaMemsetAsync(psi.p, 0, sizeof(double) * G.bessel_len, st));
-    GM_CUDA_TRY(cudaMemsetAsync(chi.p, 0, sizeof(double) * G.bessel_len, st));
+    GM_CUDA_TRY(cudaMemsetAsync(psichi.p, 0, psichi_bytes, st));
     return GM_OK;
   }
   void release() {
-    x.release(); xinv.release(); nmax.release(); gboff.release(); gk4.release(); grow.release(); psi.release(); chi.release();
+    x.release(); xinv.release(); nmax.release(); gboff.release(); gk4.release(); grow.release(); psichi.release();
   }
 };
 
@@ -440,7 +452,7 @@ extern "C" int gm_table_create(gm_handle_t h, int nx, const double* x, const int
     GM_CUDA_TRY(cudaMemcpyAsync(t->g_skip.p, t->G.gskip.data(), t->G.ngroup, cudaMemcpyHostToDevice, st));
   }
   k_bessel<<<(nx + 127) / 128, 128, 0, st>>>(nx, t->D.x.as<double>(), t->D.nmax.as<int>(), t->D.gboff.as<long long>(),
-                                             t->D.psi.as<double>(), t->D.chi.as<double>());
+                                             t->D.psi_p, t->D.chi_p);
   GM_LAUNCH_CHECK(h);
   k_pt_table<<<(GM_NANG_PAD + 127) / 128, 128, 0, st>>>(nang, t->cost.as<double>(), t->nrows, t->T.as<double>());
   GM_LAUNCH_CHECK(h);
@@ -483,8 +495,8 @@ extern "C" int gm_table_set_bessel(gm_table_t t, const int64_t* off, const doubl
   GM_CUDA_TRY(cudaMemcpyAsync(dy.p, yv_half, sizeof(double) * tot, cudaMemcpyHostToDevice, st));
   GM_CUDA_TRY(cudaMemcpyAsync(doff.p, off, sizeof(long long) * t->nx, cudaMemcpyHostToDevice, st));
   k_bessel_from_jy<<<(t->nx + 127) / 128, 128, 0, st>>>(t->nx, t->D.x.as<double>(), t->D.nmax.as<int>(), t->D.gboff.as<long long>(),
-                                                        doff.as<long long>(), dj.as<double>(), dy.as<double>(), t->D.psi.as<double>(),
-                                                        t->D.chi.as<double>());
+                                                        doff.as<long long>(), dj.as<double>(), dy.as<double>(), t->D.psi_p,
+                                                        t->D.chi_p);
   GM_LAUNCH_CHECK(h);
   GM_CUDA_TRY(cudaStreamSynchronize(st));
   dj.release(); dy.release(); doff.release();
@@ -817,6 +829,21 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
   if ((rc = ensure_ntab(h, G.nmaxmax))) return rc;
   const int64_t launches0 = h->launches;
   t->evused = 0;
+  // Experiment (GEOSMIE_L2_PERSIST=<MB>, off by default): Riccati-Bessel tables pinned in L2 for the duration of the call -- k_coeff
+  // reads one psi / chi row per order on its serial path while it streams gigabytes of coefficient rows through the same L2
+  static const int l2_persist = getenv("GEOSMIE_L2_PERSIST") ? atoi(getenv("GEOSMIE_L2_PERSIST")) : 0;
+  bool window_set = false;
+  if (l2_persist && t->D.psichi_bytes > 0 && h->l2_persist_max > 0) {
+    cudaStreamAttrValue av;
+    memset(&av, 0, sizeof(av));
+    av.accessPolicyWindow.base_ptr = t->D.psichi.p;
+    av.accessPolicyWindow.num_bytes = std::min(t->D.psichi_bytes, (size_t)h->l2_window_max);
+    av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)h->l2_persist_max / (double)av.accessPolicyWindow.num_bytes);
+    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    window_set = cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess;
+    if (!window_set) cudaGetLastError();
+  }
   if (hio) {
     if (!t->h2d_stream) {
       GM_CUDA_TRY(cudaStreamCreateWithFlags(&t->h2d_stream, cudaStreamNonBlocking));
@@ -853,8 +880,8 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
     A.x = t->D.x.as<double>();
     A.nmax = t->D.nmax.as<int>();
     A.ntab = h->ntab.as<double2>();
-    A.psi = t->D.psi.as<double>();
-    A.chi = t->D.chi.as<double>();
+    A.psi = t->D.psi_p;
+    A.chi = t->D.chi_p;
     A.gboff = t->D.gboff.as<long long>();
     A.mz = reinterpret_cast<const double2*>(d_mz) + t0;
     A.mrel = reinterpret_cast<const double2*>(d_mrel) + t0;
@@ -1069,6 +1096,12 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
     }
   }
   t->last_stats[4] = (double)(h->launches - launches0);
+  if (window_set) {
+    cudaStreamAttrValue av;
+    memset(&av, 0, sizeof(av));
+    av.accessPolicyWindow.num_bytes = 0;      // window off again for whatever else runs on the caller's stream
+    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+  }
   if (hio) {
     GM_CUDA_TRY(cudaStreamSynchronize(t->d2h_stream));
     GM_CUDA_TRY(cudaStreamSynchronize(t->h2d_stream));

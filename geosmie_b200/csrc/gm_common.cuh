@@ -60,6 +60,7 @@ struct DevBuf {
 struct gm_handle_s {
   int device = 0;
   int sm_count = 148;
+  long long l2_persist_max = 0, l2_window_max = 0;   // persisting-L2 carve-out set at gm_init, largest access-policy window
   cudaStream_t stream = nullptr;
   int64_t launches = 0;
   // scratch for the per-particle API and GSF/bands
