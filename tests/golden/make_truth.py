@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""High-precision (mpmath, 60 digits) coated-sphere efficiencies for the coated cases of mie_single.npz.
+"""High-precision (mpmath, 60 digits) coated-sphere efficiencies and S1/S2 for the coated cases of mie_single.npz.
 
 The reference evaluates coated_mie_coeff (mie_coeffs.py:183-251) with scipy's complex-argument jv/yv, whose error
 reaches ~4e-7 in a_n for |z| ~ 100 (two of the 30 golden cases are off by 3e-9 in Qext).  This fixture lets the tests
@@ -47,7 +47,8 @@ def coated_mp(eps1, eps2, x, y):
 if __name__ == "__main__":
     d = np.load(os.path.join(HERE, "mie_single.npz"))
     par = d["par"]
-    idx, q = [], []
+    idx, q, s12 = [], [], []
+    us = d["us"]
     for i in range(par.shape[0]):
         x, y = par[i, 0], par[i, 1]
         if np.isnan(y):
@@ -55,5 +56,7 @@ if __name__ == "__main__":
         an, bn, nmax = coated_mp(mp.mpc(complex(par[i, 2], par[i, 3])), mp.mpc(complex(par[i, 6], par[i, 7])), mp.mpf(x), mp.mpf(y))
         idx.append(i)
         q.append(mo.mie_props(an, bn, nmax, y))
+        # S1, S2 at the fixture's angles from the 60-digit coefficients (mie_S12_backend, mie_props.py:119-131)
+        s12.append([[v.real, v.imag, w.real, w.imag] for v, w in (mo.mie_s12(an, bn, nmax, float(u)) for u in us)])
         print(i, x, y, q[-1][:2], flush=True)
-    np.savez_compressed(os.path.join(HERE, "coated_truth.npz"), idx=np.array(idx), q=np.array(q))
+    np.savez_compressed(os.path.join(HERE, "coated_truth.npz"), idx=np.array(idx), q=np.array(q), s12=np.array(s12))

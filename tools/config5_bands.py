@@ -50,9 +50,33 @@ for sp in species:
                 nbin, nrh = a.shape[:2]
                 res[var] = bandaverage.average_columns(out["wavelength"], a.reshape(nbin * nrh, -1), "RRTMG").reshape(nbin, nrh, -1)
             t2 = time.time()
+            # parity gate: the reference's own doAverage (bandaverage.py:18-50, imported unmodified from baseline/_ref or
+            # /root/reference) on a stratified subset of the same fine-grid columns
+            parity = None
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "baseline"))
+                import ref_runner
+                os.environ["GEOSMIE_REFERENCE"] = ref_runner.reference_root()
+                import refharness
+                refharness.REF = ref_runner.reference_root()
+                RB = refharness.reference().bandaverage
+                rlo, rup, _, ruse, _ = RB.getBands("RRTMG")
+                worst, nchk = 0.0, 0
+                for var in bandaverage.varsToAverage:
+                    a = vals[var].transpose(0, 2, 1)
+                    for b_ in range(a.shape[0]):
+                        for r_ in range(0, a.shape[1], 7):
+                            for k_ in range(0, len(rlo), 3):
+                                ref = RB.doAverage(out["wavelength"], a[b_, r_], rlo[k_], rup[k_], ruse, None)
+                                got = res[var][b_, r_, k_]
+                                worst = max(worst, abs(got - ref) / max(abs(ref), 1e-300))
+                                nchk += 1
+                parity = {"checked_band_means": nchk, "max_rel_err_vs_reference_doAverage": worst}
+            except Exception as e:      # noqa: BLE001 -- reported, not hidden
+                parity = {"error": "%s: %s" % (type(e).__name__, e)}
             ncell = vals["qext"].size
             print(json.dumps({"config": 5, "species": sp, "n_lambda": nlam, "n_gpus": world, "cells": int(ncell),
-                              "table_s": t1 - t0, "bands_s": t2 - t1, "qext_band_mean": float(np.mean(res["qext"])),
+                              "table_s": t1 - t0, "bands_s": t2 - t1, "band_parity": parity, "qext_band_mean": float(np.mean(res["qext"])),
                               "finite": bool(all(np.all(np.isfinite(v)) for v in res.values()))}), flush=True)
 if comm is not None:
     comm.close()
