@@ -64,6 +64,8 @@ SIGNATURES = {
     "gm_peer_open": (C.c_int, [vp, vp, C.POINTER(vp)]),
     "gm_peer_close": (C.c_int, [vp, vp]),
     "gm_peer_put": (C.c_int, [vp, vp, vp, C.c_size_t]),
+    "gm_peer_get2d": (C.c_int, [vp, vp, C.c_size_t, vp, C.c_size_t, C.c_size_t, C.c_size_t]),
+    "gm_table_normalize_device": (C.c_int, [vp, C.c_int, vp, vp, C.POINTER(vp)]),
     "gm_peer_join": (C.c_int, [vp]),
     "gm_peer_sync": (C.c_int, [vp]),
     "gm_peer_mark": (C.c_int, [vp, C.c_int]),
@@ -173,6 +175,10 @@ class Handle:
     def peer_put(self, dst_ptr, src_ptr, nbytes):
         """Copy-engine transfer on the exchange stream, ordered after the compute stream's current work."""
         check(self.lib.gm_peer_put(self.h, vp(dst_ptr), vp(src_ptr), int(nbytes)))
+
+    def peer_get2d(self, dst_host_ptr, dpitch, src_dev_ptr, spitch, width, height):
+        """Strided device / peer -> host copy on the exchange stream (see gm_peer_get2d)."""
+        check(self.lib.gm_peer_get2d(self.h, vp(dst_host_ptr), int(dpitch), vp(src_dev_ptr), int(spitch), int(width), int(height)))
 
     def peer_join(self):
         check(self.lib.gm_peer_join(self.h))
@@ -382,6 +388,25 @@ class Table:
         self._last_psd_shape = (ntask, nmode)
         self._last_ntask = ntask
         return scal, phase
+
+    def normalize_device(self, ang_deg):
+        """k_phase_norm without the download: device pointer of the block [4][ntask][nang] (p11, p12, p33, p34) + pback4 [ntask][4]
+        and its size in bytes (valid until the next call on this table)."""
+        ntask = self._last_ntask
+        theta = np.radians(f64(ang_deg))
+        sint = np.sin(theta)
+        blk = vp()
+        check(self.lib.gm_table_normalize_device(self.t, ntask, ptr(theta), ptr(sint), C.byref(blk)))
+        return blk.value, (4 * ntask * self.nang + 4 * ntask) * 8
+
+    def fetch_pback(self, ang_deg):
+        """Only the backscatter values [ntask][4] (p11, p12, p33, p34 at the last angle) of the normalised phase matrix."""
+        ntask = self._last_ntask
+        theta = np.radians(f64(ang_deg))
+        sint = np.sin(theta)
+        pback4 = np.empty((ntask, 4))
+        check(self.lib.gm_table_fetch_normalized(self.t, ntask, ptr(theta), ptr(sint), None, None, None, None, ptr(pback4)))
+        return pback4
 
     def fetch_normalized(self, ang_deg, out=None):
         """dointegration.py:977-988 on the device-resident phase sums of the last run call: returns (p11, p12, p33, p34) [ntask][nang]

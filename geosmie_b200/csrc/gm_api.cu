@@ -1299,27 +1299,53 @@ extern "C" int gm_table_device_outputs(gm_table_t t, double** out_scal, double**
   return GM_OK;
 }
 
-extern "C" int gm_table_fetch_normalized(gm_table_t t, int ntask, const double* theta_rad, const double* sin_theta, double* p11, double* p12,
-                                         double* p33, double* p34, double* pback4) {
-  GM_REQUIRE(t && theta_rad && sin_theta && p11 && p12 && p33 && p34 && pback4, "NULL argument");
+// k_phase_norm on the device-resident phase sums of the last run: block = planes [4][ntask][nang] (when want_planes) then pback [ntask][4]
+static int normalize_on_device(gm_table_t t, int ntask, const double* theta_rad, const double* sin_theta, bool want_planes, double** planes,
+                               double** pback) {
   GM_REQUIRE(ntask > 0 && t->out_phase.p && t->out_phase.cap >= sizeof(double) * (size_t)ntask * 4 * t->nang, "no phase sums of that many tasks on the device");
   gm_handle_t h = t->h;
   GM_CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
   int rc;
   const size_t plane = (size_t)ntask * t->nang;
-  if ((rc = t->norm_planes.ensure(sizeof(double) * (4 * plane + 4 * (size_t)ntask))) || (rc = t->norm_ang.ensure(sizeof(double) * 2 * t->nang))) return rc;
+  if ((rc = t->norm_planes.ensure(sizeof(double) * ((want_planes ? 4 * plane : 0) + 4 * (size_t)ntask))) || (rc = t->norm_ang.ensure(sizeof(double) * 2 * t->nang)))
+    return rc;
   double* d_ang = t->norm_ang.as<double>();
   GM_CUDA_TRY(cudaMemcpyAsync(d_ang, theta_rad, sizeof(double) * t->nang, cudaMemcpyHostToDevice, st));
   GM_CUDA_TRY(cudaMemcpyAsync(d_ang + t->nang, sin_theta, sizeof(double) * t->nang, cudaMemcpyHostToDevice, st));
-  double* d_pl = t->norm_planes.as<double>();
-  k_phase_norm<<<ntask, GM_NANG_PAD, 0, st>>>(ntask, t->nang, t->out_phase.as<double>(), d_ang, d_ang + t->nang, d_pl, d_pl + 4 * plane);
+  *planes = want_planes ? t->norm_planes.as<double>() : nullptr;
+  *pback = t->norm_planes.as<double>() + (want_planes ? 4 * plane : 0);
+  k_phase_norm<<<ntask, GM_NANG_PAD, 0, st>>>(ntask, t->nang, t->out_phase.as<double>(), d_ang, d_ang + t->nang, *planes, *pback);
   GM_LAUNCH_CHECK(h);
-  double* dst[4] = {p11, p12, p33, p34};
-  for (int q = 0; q < 4; ++q)
-    GM_CUDA_TRY(cudaMemcpyAsync(dst[q], d_pl + (size_t)q * plane, sizeof(double) * plane, cudaMemcpyDeviceToHost, st));
-  GM_CUDA_TRY(cudaMemcpyAsync(pback4, d_pl + 4 * plane, sizeof(double) * 4 * (size_t)ntask, cudaMemcpyDeviceToHost, st));
+  return GM_OK;
+}
+
+extern "C" int gm_table_fetch_normalized(gm_table_t t, int ntask, const double* theta_rad, const double* sin_theta, double* p11, double* p12,
+                                         double* p33, double* p34, double* pback4) {
+  GM_REQUIRE(t && theta_rad && sin_theta && pback4, "NULL argument");
+  const bool want_planes = p11 != nullptr;
+  GM_REQUIRE(want_planes ? (p12 && p33 && p34) : (!p12 && !p33 && !p34), "give all four planes or none of them");
+  double *d_pl = nullptr, *d_pb = nullptr;
+  int rc = normalize_on_device(t, ntask, theta_rad, sin_theta, want_planes, &d_pl, &d_pb);
+  if (rc) return rc;
+  cudaStream_t st = t->h->stream;
+  const size_t plane = (size_t)ntask * t->nang;
+  if (want_planes) {
+    double* dst[4] = {p11, p12, p33, p34};
+    for (int q = 0; q < 4; ++q)
+      GM_CUDA_TRY(cudaMemcpyAsync(dst[q], d_pl + (size_t)q * plane, sizeof(double) * plane, cudaMemcpyDeviceToHost, st));
+  }
+  GM_CUDA_TRY(cudaMemcpyAsync(pback4, d_pb, sizeof(double) * 4 * (size_t)ntask, cudaMemcpyDeviceToHost, st));
   GM_CUDA_TRY(cudaStreamSynchronize(st));
+  return GM_OK;
+}
+
+extern "C" int gm_table_normalize_device(gm_table_t t, int ntask, const double* theta_rad, const double* sin_theta, double** block) {
+  GM_REQUIRE(t && theta_rad && sin_theta && block, "NULL argument");
+  double *d_pl = nullptr, *d_pb = nullptr;
+  int rc = normalize_on_device(t, ntask, theta_rad, sin_theta, true, &d_pl, &d_pb);
+  if (rc) return rc;
+  *block = d_pl;
   return GM_OK;
 }
 

@@ -826,8 +826,10 @@ __global__ void __launch_bounds__(GM_NANG_PAD) k_phase_norm(int ntask, int nang,
     o[0] = p11n;
 #pragma unroll
     for (int q = 1; q < 4; ++q) o[q] = p[q] * p11n / p[0];
+    if (planes) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) planes[((size_t)q * ntask + task) * nang + a] = o[q];
+      for (int q = 0; q < 4; ++q) planes[((size_t)q * ntask + task) * nang + a] = o[q];
+    }
     if (a == nang - 1) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) pback4[(size_t)task * 4 + q] = o[q];

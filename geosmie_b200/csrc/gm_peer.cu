@@ -81,6 +81,22 @@ extern "C" int gm_peer_put(gm_handle_t h, void* dst, const void* src, size_t byt
   return GM_OK;
 }
 
+// Strided read-out on the exchange stream (ordered after the compute stream): `height` rows of `width` bytes from device / peer
+// memory into host memory with a row pitch -- rank 0 scatters the segment of rank r into rows r, r + W, ... of the final table arrays.
+extern "C" int gm_peer_get2d(gm_handle_t h, void* dst_host, size_t dpitch, const void* src_dev, size_t spitch, size_t width, size_t height) {
+  GM_REQUIRE(h != nullptr && dst_host != nullptr && src_dev != nullptr, "NULL argument");
+  GM_REQUIRE(dpitch >= width && spitch >= width, "pitch smaller than the row width");
+  if (width == 0 || height == 0) return GM_OK;
+  GM_CUDA_TRY(cudaSetDevice(h->device));
+  int rc = peer_streams(h);
+  if (rc) return rc;
+  GM_CUDA_TRY(cudaEventRecord(h->peer_ev_compute, h->stream));
+  GM_CUDA_TRY(cudaStreamWaitEvent(h->peer_stream, h->peer_ev_compute, 0));
+  GM_CUDA_TRY(cudaMemcpy2DAsync(dst_host, dpitch, src_dev, spitch, width, height, cudaMemcpyDeviceToHost, h->peer_stream));
+  h->peer_pending = true;
+  return GM_OK;
+}
+
 extern "C" int gm_peer_join(gm_handle_t h) {
   GM_REQUIRE(h != nullptr, "handle is NULL");
   if (!h->peer_pending) return GM_OK;

@@ -696,27 +696,42 @@ def fun(partID0, datatype, oppfx, oppclassic, elide=True, write=True, comm=None,
         ncell = len(plan.cells)
         li = np.array([c[0] for c in plan.cells], dtype=np.int64)
         ri = np.array([c[1] for c in plan.cells], dtype=np.int64)
-        ret, in_place = None, False
+        ret, in_place, phase_block, table = None, False, None, None
+        # Multi-GPU with the phase matrices normalised on the device: the block of every rank goes to rank 0's peer-mapped buffer
+        # straight from device memory and rank 0 reads every segment with ONE strided copy per plane into rows r, r + W, ... of the
+        # final arrays -- no host staging, no row matrix, no scatter (decided identically on every rank)
+        peer_phase = False
+        if world > 1 and keep_phase and plan.device_psd and plan.nri == 1:
+            nrr = 1 if trivial else nr
+            seg_bytes = (4 * na + 4) * 8 * ((nl + world - 1) // world) * nrr
+            pg = comm.peer_gather(seg_bytes)
+            peer_phase = pg is not None
         if ncell:
             table = _lib.Table(plan.xx, plan.nmax, costarr)
             # One task per cell and weights made on the device (every shipped Mie species except the 'du' grid and multi-index
             # bins): the a-posteriori normalisation runs on the GPU (k_phase_norm) and the four distinct phase-matrix planes arrive
             # normalised -- straight in their final arrays when this rank owns the whole bin in file order (one GPU).
-            on_device = plan.device_psd and plan.nri == 1 and keep_phase
+            on_device = plan.device_psd and plan.nri == 1
             scal, phase, tpc = plan.evaluate(table, elide=elide, phase_on_device=on_device)
             ret = plan.reduce(scal, phase, tpc)
             if phase is None:
-                in_place = world == 1 and ncell == nl * nr
-                dst = [vals[k][radind].reshape(ncell, na) for k in ('p11', 'p12', 'p33', 'p34')] if in_place else None
-                planes, pb = table.fetch_normalized(ang, out=dst)
                 ret['lidar_ratio'] = ret['qext'] / ret['qb'] * 4 * np.pi
                 ret['ssa'] = ret['qsca'] / ret['qext']
-                ret['p11'], ret['p12'], ret['p33'], ret['p34'] = planes
-                ret['p22'], ret['p44'] = planes[0], planes[2]          # spheres (calculateScatVals, dointegration.py:1044-1050)
-                ret['pback'] = pb[:, [0, 1, 2, 3, 0, 2]]
+                in_place = world == 1 and ncell == nl * nr                 # this rank owns the whole bin, cells in file order
+                if keep_phase and peer_phase:
+                    phase_block = table.normalize_device(ang)         # stays on the GPU: it travels to rank 0 over NVLink below
+                    pb = None
+                elif keep_phase:
+                    dst = [vals[k][radind].reshape(ncell, na) for k in ('p11', 'p12', 'p33', 'p34')] if in_place else None
+                    planes, pb = table.fetch_normalized(ang, out=dst)
+                    ret['p11'], ret['p12'], ret['p33'], ret['p34'] = planes
+                    ret['p22'], ret['p44'] = planes[0], planes[2]      # spheres (calculateScatVals, dointegration.py:1044-1050)
+                else:
+                    pb = table.fetch_pback(ang)                        # the phase matrices never leave the GPU
+                if pb is not None:
+                    ret['pback'] = pb[:, [0, 1, 2, 3, 0, 2]]
             else:
                 ret = postprocess(ret, ang)
-            table.close()
             # mass0 = volume(RH index 0) * rhop0 of the same (bin, lambda) (dointegration.py:992-997)
             vol0 = np.zeros(nl)
             sel0 = ri == 0
@@ -730,9 +745,42 @@ def fun(partID0, datatype, oppfx, oppclassic, elide=True, write=True, comm=None,
             ret['rUp'] = plan.rUp
             ret['refreal'] = plan.m[:, 0].real
             ret['refimag'] = -np.abs(plan.m[:, 0].imag)
+        if peer_phase:
+            if phase_block is not None:
+                pg.put(0, phase_block[0], phase_block[1])
+            pg.complete()                                          # every rank's block has landed in rank 0's buffer
+            if rank == 0:
+                h0 = pg.h
+                row = nrr * na * 8                                 # one wavelength of one plane: nrr RH x na angles
+                pbs = []
+                for r in range(world):
+                    nlr = len(range(r, nl, world))
+                    ncr = nlr * nrr
+                    if ncr == 0:
+                        pbs.append(np.zeros((0, 4)))
+                        continue
+                    seg = pg.seg_ptr(0, 0, rank=r)
+                    for q, key in enumerate(('p11', 'p12', 'p33', 'p34')):
+                        dst = vals[key][radind, r]                 # rows r, r + W, ... of (wavelength, rh, ang)
+                        h0.peer_get2d(dst.ctypes.data, world * nr * na * 8, seg + q * ncr * na * 8, row, row, nlr)
+                    pbr = np.empty((ncr, 4))
+                    h0.peer_put(pbr.ctypes.data, seg + 4 * ncr * na * 8, pbr.nbytes)
+                    pbs.append(pbr)
+                h0.peer_sync()
+                for r in range(world):
+                    if pbs[r].shape[0]:
+                        vals['pback'][radind, r::world, :nrr] = pbs[r][:, [0, 1, 2, 3, 0, 2]].reshape(-1, nrr, 6)
+                vals['p22'][radind] = vals['p11'][radind]
+                vals['p44'][radind] = vals['p33'][radind]
+            comm.barrier()                                         # the buffer may be reused (next bin) only now
+        if table is not None:
+            table.close()
         if world > 1:
-            # only the distinct columns travel: p22 / p44 are rebuilt from p11 / p33 on rank 0 when the device normalised them
+            # only the distinct columns travel: p22 / p44 are rebuilt from p11 / p33 on rank 0 when the device normalised them;
+            # with the peer path above the phase matrices and pback have already arrived
             dup = {'p22': 'p11', 'p44': 'p33'} if (plan.device_psd and plan.nri == 1 and keep_phase) else {}     # same on every rank
+            if peer_phase:
+                dup = {k: None for k in scatkeys + ['pback']}
             send = [k for k in keys if k not in dup]
             rows = np.zeros((ncell, 2 + sum(width[k] for k in send)))
             if ncell:
@@ -750,9 +798,12 @@ def fun(partID0, datatype, oppfx, oppclassic, elide=True, write=True, comm=None,
                 ret[k] = rows[:, o:o + width[k]] if width[k] > 1 else rows[:, o]
                 o += width[k]
             for k, src in dup.items():
-                ret[k] = ret[src]
+                if src is not None:
+                    ret[k] = ret[src]
         if ret is not None:
             for key in keys:
+                if key not in ret:
+                    continue                                   # arrived through the peer path
                 col = np.asarray(ret[key])
                 if _kind_of(key) == "nl":
                     # (bin, rh) variables are overwritten at every wavelength: the last one wins (dointegration.py:1026-1027)

@@ -89,3 +89,22 @@ def write_run_dir(d, sp, fixture=DEFAULT_FIXTURE):
         with open(path, "w") as fp:
             fp.write(text)
     return sp + ".json"
+
+
+def fine_grid_files(sp, nlam=2048, fixture=DEFAULT_FIXTURE):
+    """BASELINE config 5: the species table on a FINE spectral grid -- its refractive-index spectrum resampled to `nlam` log-spaced
+    wavelengths by linear interpolation (what interp1d would return).  {relative path: text} for a run directory and the
+    name of the configuration file."""
+    g = np.load(fixture)
+    ml, w = g[sp + "__mlist"], g["su__water"]
+    lam = np.geomspace(ml[0][0], ml[0][-1], nlam)
+    lam[0], lam[-1] = ml[0][0], ml[0][-1]
+    n, k = np.interp(lam, ml[0], ml[1]), np.interp(lam, ml[0], ml[2])
+    cfg = json.loads(json.dumps(SPECIES[sp]))
+    cfg.pop("hydrophobic", None)
+    cfg["ri"] = {"format": "wsv", "path": ["ri-%s-fine.wsv" % sp]}
+    files = species_files(sp, fixture)
+    files = {os.path.join("data", "refrac.water.txt"): files[os.path.join("data", "refrac.water.txt")],
+             sp + "_fine.json": json.dumps(cfg),
+             "ri-%s-fine.wsv" % sp: "\n".join("%.17g %.17g %.17g" % (l * 1e6, a, b) for l, a, b in zip(lam, n, k)) + "\n"}
+    return files, sp + "_fine.json"

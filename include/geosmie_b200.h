@@ -164,9 +164,14 @@ int gm_table_device_outputs(gm_table_t t, double** out_scal, double** out_phase)
  *   I = trapz(p11 sin(theta), theta);  p11n = 2 p11 / I;  pXX = pXX p11n / p11 for XX = 12, 33, 34;  pback = the values at the
  *   last angle.  theta_rad, sin_theta [nang] (host; the caller's own sin values, so the products match the reference's bits).
  * Host outputs, each one CONTIGUOUS plane: p11, p12, p33, p34 [ntask][nang] (the caller's final arrays: p22 = p11 and p44 = p33
- * for spheres), pback4 [ntask][4] in the order 11, 12, 33, 34.  The trapezoid sum is taken in a fixed order (deterministic). */
+ * for spheres), pback4 [ntask][4] in the order 11, 12, 33, 34.  The four plane pointers may all be NULL: only pback4 is delivered
+ * (tables whose phase matrices are not kept, e.g. fine spectral grids for band averaging).  The trapezoid sum is taken in a fixed
+ * order (deterministic). */
 int gm_table_fetch_normalized(gm_table_t t, int ntask, const double* theta_rad, const double* sin_theta, double* p11, double* p12,
                               double* p33, double* p34, double* pback4);
+/* The same normalisation without the download: *block = device pointer of [4][ntask][nang] (p11, p12, p33, p34) followed by
+ * pback4 [ntask][4], valid until the next call on this table -- the source of a multi-GPU gm_peer_put. */
+int gm_table_normalize_device(gm_table_t t, int ntask, const double* theta_rad, const double* sin_theta, double** block);
 /* per-particle outputs through the table (DMMA) path: q [ntask][nx][6], s12 [ntask][nx][nang][4] (host pointers) */
 int gm_table_particles(gm_table_t t, int ntask, const double* mz, const double* mrel, double* q, double* s12);
 /* statistics of the last gm_table_run*: [0] particle evaluations, [1] sum of nmax over evaluated particles,
@@ -242,6 +247,9 @@ int gm_peer_free(gm_handle_t h, void* dptr);
 int gm_peer_open(gm_handle_t h, const unsigned char ipc_handle[GM_IPC_HANDLE_BYTES], void** dptr);
 int gm_peer_close(gm_handle_t h, void* dptr);
 int gm_peer_put(gm_handle_t h, void* dst, const void* src, size_t bytes);
+/* strided read-out on the exchange stream: `height` rows of `width` bytes, device / peer memory -> host memory with row pitch
+ * `dpitch` (rank 0 scatters the segment of rank r into rows r, r + W, ... of the final table arrays in ONE pass) */
+int gm_peer_get2d(gm_handle_t h, void* dst_host, size_t dpitch, const void* src_dev, size_t spitch, size_t width, size_t height);
 int gm_peer_join(gm_handle_t h);
 int gm_peer_sync(gm_handle_t h);
 int gm_peer_mark(gm_handle_t h, int idx);
