@@ -50,10 +50,82 @@ def expand_table(ang, elements, oppclassic, quantize=True, handle=None):
     return pm
 
 
+NUM_GAUSS_LEGENDRE = 960              # num_gauss, convertncdf.py:323 (spher_expan.x accepts fewer than 1000 input angles)
+
+
+def hbleg(x, pmoms):
+    """sum_l pmoms[..., l] P_l(x) with the reference's recurrence (convertncdf.py:31-43), vectorised: pmoms [..., nmom], x [nx]
+    -> [..., nx].  (The stored Legendre moments carry their own normalisation: no (2l+1) factor is applied.)"""
+    x = np.asarray(x, dtype=float)
+    nmom = pmoms.shape[-1]
+    leg = np.zeros((nmom, x.size))
+    leg[0] = 1.
+    if nmom > 1:
+        leg[1] = x
+    for imom in range(2, nmom):
+        leg[imom] = 1. / imom * ((2. * imom - 1.) * x * leg[imom - 1] - (imom - 1.) * leg[imom - 2])
+    return np.asarray(pmoms, dtype=float) @ leg
+
+
+def process_legendre(nc, quantize=True, handle=None):
+    """rungsf mode 'legendre' (convertncdf.py:190-219, :46-67, :377-394): a legacy table whose `pmom (nPol, nMom, radius, rh, lambda)`
+    holds LEGENDRE moments of the six elements.  Every cell's series is evaluated at the 960 Gauss angles (the input the expansion
+    program gets) and at 181 linear angles, all cells are expanded in one GPU call, and the file receives
+        pmom2         the original Legendre moments,
+        pmom          the generalized-spherical-function moments, zero-padded to nMom,
+        phase_matrix  (nPol, scattering_angle, radius, rh, lambda) and scattering_angle = 0..180 degrees.
+    The reference indexes pmom2 / phase_matrix with the new-style order although it creates them with the legacy dimensions
+    (:379, :392) and stops with an index error on its own files; the variables are written here as they are dimensioned."""
+    from numpy.polynomial.legendre import leggauss
+    pm = np.array(nc.variables['pmom'][:])                    # (nPol, nMom, radius, rh, lambda)
+    npol, nmom, nrad, nrh, nlam = pm.shape
+    linangs = np.linspace(0, 180, 181)
+    gpoints, _ = leggauss(NUM_GAUSS_LEGENDRE)
+    gpoints = gpoints[::-1]
+    gdeg = np.degrees(np.arccos(gpoints))
+    moms = pm.transpose(2, 3, 4, 0, 1)                        # (radius, rh, lambda, nPol, nMom)
+    order = NPOL_OF_COLUMN                                    # Mishchenko's column ii <- nPol index (convertncdf.py:201)
+    F = hbleg(gpoints, moms[..., order, :]).reshape(nrad * nrh * nlam, 6, NUM_GAUSS_LEGENDRE)
+    lin = hbleg(np.cos(np.radians(linangs)), moms)            # (radius, rh, lambda, nPol, 181), nPol order as stored
+    h = handle or _lib.Handle.get()
+    coef, _ = h.gsf_expand(gdeg, F, NUM_EXPAND, quantize10=quantize)
+    coef = coef.reshape(nrad, nrh, nlam, 6, NUM_EXPAND)
+    new = np.zeros((npol, nmom, nrad, nrh, nlam))
+    nkeep = min(nmom, NUM_EXPAND)
+    for ii, p_ in enumerate(order):
+        new[p_, :nkeep] = coef[..., ii, :nkeep].transpose(3, 0, 1, 2)
+    nc.createVariable('pmom2', 'f8', ('nPol', 'nMom', 'radius', 'rh', 'lambda'))
+    nc.createDimension('nMom-GSF', NUM_EXPAND)
+    nc.variables['pmom2'].long_name = getattr(nc.variables['pmom'], 'long_name', '')
+    nc.variables['pmom2'][:] = pm
+    nc.variables['pmom'].long_name = PMOM_LONG_NAME
+    nc.variables['pmom'][:] = new
+    nc.createDimension('scattering_angle', linangs.size)
+    nc.createVariable('scattering_angle', 'f8', ('scattering_angle'))
+    nc.variables['scattering_angle'][:] = linangs
+    nc.variables['scattering_angle'].long_name = 'Scattering angle in degrees'
+    nc.createVariable('phase_matrix', 'f8', ('nPol', 'scattering_angle', 'radius', 'rh', 'lambda'))
+    nc.variables['phase_matrix'].long_name = 'Phase matrix elements, ordered over nPol as P11, P12, P33, P34, P22, P44'
+    nc.variables['phase_matrix'][:] = lin.transpose(3, 4, 0, 1, 2)
+    return new
+
+
 def processFileRaw(infile, outdir, whichproc, rhop0, mode, ice, quantize=True):
     """Copy <name>.nomom.nc4 to <name>.nc4 and add pmom (convertncdf.py:319-401)."""
-    if mode != 'pygeos':
-        raise NotImplementedError("rungsf mode %r reads a foreign table format; only 'pygeos' is on the Mie hot path" % mode)
+    if mode not in ('pygeos', 'legendre') or ice:
+        raise NotImplementedError("rungsf mode %r reads a foreign table format (ice crystals / GRASP kernels) that is outside the Mie "
+                                  "hot path; 'pygeos' and 'legendre' are available" % ('ice' if ice else mode))
+    if mode == 'legendre':
+        fn = os.path.basename(infile)
+        outfile = os.path.join(outdir, fn.replace('nomom.', ''))
+        if os.path.abspath(outfile) != os.path.abspath(infile):
+            shutil.copyfile(infile, outfile)
+        nc = ncio.Dataset(outfile, 'r+')
+        print('mode %s' % mode)
+        process_legendre(nc, quantize=quantize)
+        nc.close()
+        print("%s done" % fn)
+        return outfile
     fn = os.path.basename(infile)
     outfile = os.path.join(outdir, fn.replace('nomom.', ''))
     shutil.copyfile(infile, outfile)

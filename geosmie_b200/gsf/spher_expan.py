@@ -8,13 +8,17 @@ Writes, like main of src/gsf/spher_expan.f (:84-107),
     <file>.expan_matr    the matrix re-synthesised from the coefficients, '(F6.2,X,4E15.5,2F11.5)'
 and prints `NG fiterr` and `FINAL NG ... Error ...` (:63-66, :83).  The arithmetic runs on the GPU (gm_gsf_diagnose): all
 files given on the command line are expanded in ONE call when they share the angle grid, instead of one process per cell.
-NSPHER = 129 > 0 (params.h:14), so the adaptive NG loop of the Fortran main (:67-82) never runs; it is not reproduced.
+NSPHER = 129 > 0 (params.h:14), so the adaptive NG loop of the Fortran main (:67-82) never runs in the reference build; it is
+available here as `--nspher 0` (what a rebuild with NSPHER <= 0 would do): NG starts at MIN_NSPHER = 129 and grows by DELTA_NG = 10
+until the fit error is <= DESIRED_ERR = 0.02 (params.h:9-15), every file with its own final NG.
 """
 import sys
 
 import numpy as np
 
 NSPHER = 129      # params.h:14
+MIN_NSPHER, DELTA_NG, DESIRED_ERR = 129, 10, 0.02      # params.h:15, :12, :11
+NG_LIMIT = 2048   # largest number of Gauss nodes of the device kernels (the Fortran arrays allow NG_MAX = 100000)
 
 
 def fortran_f(v, w, d):
@@ -81,27 +85,61 @@ def expand_files(paths, handle=None, ng=NSPHER):
                 np.array_equal(data[j][:, 0], data[i][:, 0])]
         ang = data[i][:, 0]
         F = np.stack([data[j][:, 1:].T for j in same])
-        coef, cn, fout, fiterr = h.gsf_diagnose(ang, F, ng)
-        for k, j in enumerate(same):
+        if ng > 0:
+            coef, cn, fout, fiterr = h.gsf_diagnose(ang, F, ng)
+            res = [(ng, [(ng, float(fiterr[k]))], coef[k], cn[k], fout[k], float(fiterr[k])) for k in range(len(same))]
+        else:
+            res = expand_adaptive(h, ang, F)
+        for (ngk, trail, coefk, cnk, foutk, errk), j in zip(res, same):
             done[j] = True
             print(paths[j])
-            print(" %11d  %s" % (ng, repr(float(fiterr[k]))))
-            print(" FINAL NG %11d Error  %s" % (ng, repr(float(fiterr[k]))))
+            for n_, e_ in trail:
+                print(" %11d  %s" % (n_, repr(e_)))
+            print(" FINAL NG %11d Error  %s" % (ngk, repr(errk)))
             with open(paths[j] + ".expan_matr", "w") as f:
-                f.write(format_expan_matr(ang, fout[k]))
+                f.write(format_expan_matr(ang, foutk))
             with open(paths[j] + ".expan_coeff", "w") as f:
-                f.write(format_expan_coeff(coef[k], cn[k]))
-            out[paths[j]] = float(fiterr[k])
+                f.write(format_expan_coeff(coefk, cnk))
+            out[paths[j]] = errk
     return out
+
+
+def expand_adaptive(h, ang, F, min_ng=MIN_NSPHER, delta=DELTA_NG, desired=DESIRED_ERR, limit=NG_LIMIT):
+    """The NSPHER <= 0 branch of the Fortran main (spher_expan.f:67-82) for a batch of matrices on one angle grid: every matrix is
+    expanded with NG = min_ng, min_ng + delta, ... until its fit error (one_calc) is <= desired; matrices still above the threshold go
+    to the GPU together at the next NG.  Returns per matrix (final NG, [(NG, fiterr), ...], coef [6][NG], cnorm, fout [6][nang], fiterr)."""
+    n = F.shape[0]
+    res = [None] * n
+    trail = [[] for _ in range(n)]
+    pending = list(range(n))
+    ng = min_ng
+    while pending:
+        coef, cn, fout, fiterr = h.gsf_diagnose(ang, F[pending], ng)
+        still = []
+        for k, j in enumerate(pending):
+            e = float(fiterr[k])
+            trail[j].append((ng, e))
+            if e <= desired or ng + delta > limit:
+                res[j] = (ng, trail[j], coef[k], float(cn[k]), fout[k], e)
+            else:
+                still.append(j)
+        pending = still
+        ng += delta
+    return res
 
 
 def main(argv=None):
     argv = sys.argv[1:] if argv is None else argv
+    ng = NSPHER
+    if "--nspher" in argv:                      # the reference fixes NSPHER at compile time (params.h:14); <= 0 selects the adaptive loop
+        k = argv.index("--nspher")
+        ng = int(argv[k + 1])
+        argv = argv[:k] + argv[k + 2:]
     if len(argv) < 1:
         print(" Wrong number of arguments: %d" % len(argv))
-        print(" Usage: spher_expan <filename> [<filename> ...]")
+        print(" Usage: spher_expan [--nspher N] <filename> [<filename> ...]")
         return 1
-    expand_files(argv)
+    expand_files(argv, ng=ng)
     return 0
 
 
