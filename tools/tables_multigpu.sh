@@ -21,7 +21,7 @@ export PYTHONPATH=$ROOT
 {
 echo "# $(nvidia-smi --query-gpu=name --format=csv,noheader | head -1) x $N, $(date -u +%FT%TZ)"
 port=29700
-for rep in 1 2; do
+for rep in $(seq 1 ${REPS:-2}); do
 for sp in su bc ss; do
   mkdir -p out_$rep
   port=$((port + 1))
@@ -39,6 +39,6 @@ for sp in su bc ss; do
   [ $rc -ne 0 ] && tail -5 log_$sp.txt
 done
 done
-python $ROOT/tools/check_tables.py out_2 su bc ss
+python $ROOT/tools/check_tables.py out_${REPS:-2} su bc ss
 } 2>&1 | tee $OUT
 cd $ROOT; rm -rf "$D"
