@@ -28,6 +28,9 @@
 #define GM_SMALL_SEG0 16         // k_small: particle groups per work item (warp), class 0 (max nmax <= 4) / class 1 (max nmax <= 8)
 #define GM_SMALL_SEG1 8
 #endif
+#ifndef GM_GRAM_ITEMS_PER_SM
+#define GM_GRAM_ITEMS_PER_SM 6   // k_gram: work items (class x task range) per SM, launched longest first
+#endif
 #ifndef GM_EVAL_CTAS_PER_SM
 #define GM_EVAL_CTAS_PER_SM 2    // k_gram_eval: CTAs (angle block x task range) per SM
 #endif
@@ -230,10 +233,11 @@ struct DevGroups {
     if ((rc = gboff.ensure(sizeof(long long) * G.ngroup))) return rc;
     if ((rc = gk4.ensure(sizeof(int) * G.ngroup))) return rc;
     if ((rc = grow.ensure(sizeof(int) * G.ngroup))) return rc;
-    if ((rc = psichi.ensure(sizeof(double) * 2 * G.bessel_len))) return rc;     // psi | chi in ONE allocation (one L2 access-policy window)
-    psi_p = psichi.as<double>();
-    chi_p = psi_p + G.bessel_len;
-    psichi_bytes = sizeof(double) * 2 * (size_t)G.bessel_len;
+    const size_t slack = (size_t)GM_BESSEL_SLACK_ROWS * GM_GROUP;                // doubles of slack around each table (k_coeff's unchecked ring)
+    psichi_bytes = sizeof(double) * 2 * ((size_t)G.bessel_len + 2 * slack);
+    if ((rc = psichi.ensure(psichi_bytes))) return rc;                           // psi | chi in ONE allocation
+    psi_p = psichi.as<double>() + slack;
+    chi_p = psi_p + G.bessel_len + 2 * slack;
     GM_CUDA_TRY(cudaMemcpyAsync(x.p, hx, sizeof(double) * G.nx, cudaMemcpyHostToDevice, st));
     GM_CUDA_TRY(cudaMemcpyAsync(nmax.p, hnmax, sizeof(int) * G.nx, cudaMemcpyHostToDevice, st));
     GM_CUDA_TRY(cudaMemcpyAsync(gboff.p, G.gboff.data(), sizeof(long long) * G.ngroup, cudaMemcpyHostToDevice, st));
@@ -362,7 +366,8 @@ extern "C" int gm_mie_eval(gm_handle_t h, int n, const double* x, const double* 
     A.aboff = W[7].as<long long>();
     A.ab = W[8].as<double4>();
     A.q = W[9].as<double>();
-    dim3 grid((G.ngroup + 3) / 4, 1);
+    GM_REQUIRE((G.ngroup + 3) / 4 <= 65535, "more than 8.3 million particles in one gm_mie_eval call: split the call");
+    dim3 grid(1, (G.ngroup + 3) / 4);      // x = task, y = quad of groups (see k_coeff)
     A.ntask = 1;
     k_coeff<1><<<grid, 128, 0, st>>>(A);
     GM_LAUNCH_CHECK(h);
@@ -426,6 +431,7 @@ extern "C" int gm_table_create(gm_handle_t h, int nx, const double* x, const int
   GM_REQUIRE(cos_theta != nullptr, "cos_theta is NULL");
   int rc = check_particles(nx, x, nmax);
   if (rc) return rc;
+  GM_REQUIRE(nx <= 65535 * 128, "more than 8.3 million grid points in one table");     // k_coeff: one grid.y entry per 4 groups of 32
   GM_CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
   gm_table_s* t = new gm_table_s();
@@ -601,7 +607,7 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
   const size_t per_task_bytes = (size_t)task_stride * 8;
   int tb = (int)std::max<size_t>(1, h->coef_budget_bytes / std::max<size_t>(per_task_bytes, 1));
   tb = std::min(tb, ntask);
-  tb = std::min(tb, 32768);  // grid.y limit of k_coeff
+  tb = std::min(tb, 32768);  // tasks per launch
   if (d_core_ratio) {
     // coated spheres: natural-layout a_n, b_n + recurrence scratch per (task, particle) are staged in HBM
     const size_t per_task = (size_t)t->c_nab * sizeof(double4) + (size_t)t->c_nscr * 8 * sizeof(double);
@@ -649,7 +655,7 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
   const bool use_gram = !per_particle && !(flags & GM_F_NO_GRAM) && !G.glist.empty();
   // fused coefficient + Gram kernel for the groups with max nmax <= 8 (gm_small.cuh): homogeneous spheres, one PSD mode
   static const bool small_off = getenv("GEOSMIE_NO_SMALL") != nullptr;     // diagnostics: the round-1 path (k_coeff + k_gram) for every class
-  const bool use_small = use_gram && nmode == 1 && !d_core_ratio && !small_off && G.cls_begin[2] > 0;
+  const bool use_small = use_gram && nmode == 1 && !d_core_ratio && !d_q && !small_off && G.cls_begin[2] > 0;   // (k_small has no per-particle q output)
   std::vector<SmallSeg> small_segs;
   const int ndirect = use_gram ? G.ndirect : G.ngroup;
   // chunks of the per-angle contraction: enough CTAs to fill the machine ~8x over, cost-balanced by the k4 steps of the
@@ -712,7 +718,7 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
         if (use_small && c <= 1) continue;   // not k_gram's work
         total += ccost[c] * nt;
       }
-      const double target = std::max(total / (h->sm_count * 6.0), 12000.0);
+      const double target = std::max(total / (h->sm_count * (double)GM_GRAM_ITEMS_PER_SM), 12000.0);
       std::vector<std::pair<double, GramItem>> items;
       for (int c = 0; c <= GM_GRAM_MAX_TG; ++c) {
         const int nc = G.cls_begin[c + 1] - G.cls_begin[c];
@@ -918,13 +924,13 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
       A.aboff = t->c_aboff.as<long long>();
       A.ab = t->c_ab.as<double4>();
       A.ab_stride = t->c_nab;
-      k_coeff<2><<<dim3((G.ngroup + 3) / 4, (nt + GM_COEFF_TPC - 1) / GM_COEFF_TPC), 128, 0, st>>>(A);
+      k_coeff<2><<<dim3((nt + GM_COEFF_TPC - 1) / GM_COEFF_TPC, (G.ngroup + 3) / 4), 128, 0, st>>>(A);
     } else if (use_small) {
       A.gsel = t->s_big.as<int>();
       A.nsel = (int)big_groups.size();
-      if (A.nsel > 0) k_coeff<0><<<dim3((A.nsel + 3) / 4, (nt + GM_COEFF_TPC - 1) / GM_COEFF_TPC), 128, 0, st>>>(A);
+      if (A.nsel > 0) k_coeff<0><<<dim3((nt + GM_COEFF_TPC - 1) / GM_COEFF_TPC, (A.nsel + 3) / 4), 128, 0, st>>>(A);
     } else {
-      k_coeff<0><<<dim3((G.ngroup + 3) / 4, (nt + GM_COEFF_TPC - 1) / GM_COEFF_TPC), 128, 0, st>>>(A);
+      k_coeff<0><<<dim3((nt + GM_COEFF_TPC - 1) / GM_COEFF_TPC, (G.ngroup + 3) / 4), 128, 0, st>>>(A);
     }
     GM_LAUNCH_CHECK(h);
     if ((rc = ev_mark(t, 0))) return rc;

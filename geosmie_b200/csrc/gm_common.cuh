@@ -97,6 +97,7 @@ constexpr int GM_LAH = 194;           // doubles per table row per half (192 + 2
 constexpr int GM_TROW = 2 * GM_LAH;   // p_n row then q_n row
 constexpr int GM_SB = 132;            // doubles per coefficient row: 64 (c+) + 64 (c-) + 4 pad (stride 4 mod 16 -> conflict-free B fragments)
 constexpr int GM_KSTEP = 4;           // DMMA k extent
+constexpr int GM_BESSEL_SLACK_ROWS = 8;   // rows of 32 doubles in front of and behind the psi and chi tables: k_coeff's ring reads them unchecked
 constexpr int GM_STAGE_DBL = GM_KSTEP * GM_TROW + GM_KSTEP * GM_SB;
 #ifndef GM_PRODUCER_WARP
 #define GM_PRODUCER_WARP 1   // 1: dedicated TMA producer warp (4th warpgroup, setmaxnreg); 0: thread 0 of warp 0 produces

@@ -261,6 +261,9 @@ __device__ __forceinline__ void gram_cta(const GramArgs& A, const GramItem it, c
   }
 }
 
+// 128 registers (220 B of spills in the widest instantiations) is the ceiling: the 13 warps of the CTA land 4 / 3 / 3 / 3 on the four SM
+// sub-partitions, and four warps of 144 registers (the next step, which would not spill) exceed one sub-partition's 16,384-register file --
+// a __maxnreg__(144) build fails at launch with "too many resources requested".
 __global__ void __launch_bounds__(GM_GRAM_THREADS, 1) k_gram(GramArgs A) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* ring = reinterpret_cast<double*>(smem_raw);

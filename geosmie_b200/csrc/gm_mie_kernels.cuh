@@ -188,19 +188,23 @@ struct CoeffArgs {
 #define GM_COEFF_SHORT_START 0
 #endif
 #ifndef GM_COEF_STCS
-#define GM_COEF_STCS 0
+#define GM_COEF_STCS 1   // coefficient stream written with st.global.cs (evict-first): optics_SS k_coeff 120.6 -> 101.9 ms, optics_SU unchanged
 #endif
+// Grid: x = task (fastest: CTAs that are resident together work on the same four groups of consecutive tasks and share their Bessel rows
+// through L1 / L2), y = quad of groups in DESCENDING order -- on a sorted size grid the cost of a group grows with its index (nmax ~ x), so
+// the longest CTAs start first and the last wave holds the cheapest ones.  (Round 1 / early round 2: x = quad ascending, y = task; ncu of an
+// optics_SS bin-5 launch showed the SMs active 74 % of the elapsed cycles: the tail was the largest groups of the last tasks.)
 #if GM_COEFF_TPC == 1
-#define GM_COEFF_TASK_LOOP const int task = blockIdx.y;
+#define GM_COEFF_TASK_LOOP const int task = blockIdx.x;
 #define GM_COEFF_NEXT_TASK return
 #else
 #define GM_COEFF_TASK_LOOP \
-  for (int task = blockIdx.y * GM_COEFF_TPC; task < min(A.ntask, (int)(blockIdx.y + 1) * GM_COEFF_TPC); ++task)
+  for (int task = blockIdx.x * GM_COEFF_TPC; task < min(A.ntask, (int)(blockIdx.x + 1) * GM_COEFF_TPC); ++task)
 #define GM_COEFF_NEXT_TASK continue
 #endif
 template <int MODE>
 __global__ void __launch_bounds__(128, GM_COEFF_MINB) k_coeff(CoeffArgs A) {
-  int g = blockIdx.x * 4 + (threadIdx.x >> 5);
+  int g = (int)(gridDim.y - 1 - blockIdx.y) * 4 + (threadIdx.x >> 5);
   if (A.gsel) {
     if (g >= A.nsel) return;
     g = A.gsel[g];
@@ -272,7 +276,11 @@ __global__ void __launch_bounds__(128, GM_COEFF_MINB) k_coeff(CoeffArgs A) {
   double qpsi[PD], qchi[PD];
 #pragma unroll
   for (int k = 0; k < PD; ++k) qpsi[k] = qchi[k] = 0.0;
+#ifndef GM_COEFF_BRANCHY
+  if (act && MODE == 1) {
+#else
   if (act && MODE != 2) {
+#endif
     psi_n = A.psi[bbase + (size_t)nm * 32];
     chi_n = A.chi[bbase + (size_t)nm * 32];
 #pragma unroll
@@ -299,7 +307,92 @@ __global__ void __launch_bounds__(128, GM_COEFF_MINB) k_coeff(CoeffArgs A) {
       tt = make_double2(fma(f2, zinv.x, -ti.x), fma(f2, zinv.y, -ti.y));
     }
   }
-  // ---- phase 2: orders that emit coefficients
+#ifndef GM_COEFF_BRANCHY
+  if constexpr (MODE == 0) {
+    // ---- phase 2, table mode (round 2): ONE branch-free loop body.  The round-1 body below has two divergent regions per order (177
+    // SASS instructions and two BSSY / BSYNC pairs per order); here every lane computes every order of the group's tile and selects
+    // decide what counts: `on` = the lane's recurrence has started (n < nmx), `emit` = the order exists for the lane (n <= nmax).  The
+    // Riccati-Bessel values come from a PD-deep ring that is loaded for every lane whatever its own nmax (rows up to the group's largest
+    // nmax exist in the table; rows above a lane's nmax hold zeros), so the loads never depend on a predicate of the arithmetic.
+    // No bounds checks on the ring loads: the tables have GM_BESSEL_SLACK_ROWS rows of slack at both ends, rows above the group's
+    // largest nmax belong to the next group and rows below 0 to the previous one -- what is read there only ever feeds orders that no
+    // lane emits (n > nmax) or that do not exist (n < 1).
+    const double* pp = A.psi + bbase + (size_t)(n - 1) * 32;     // row of order n - 1
+    const double* pc = A.chi + bbase + (size_t)(n - 1) * 32;
+    double rp[PD], rc[PD];
+#pragma unroll
+    for (int k = 0; k < PD; ++k) {
+      rp[k] = pp[-k * 32];
+      rc[k] = pc[-k * 32];
+    }
+    double psi_c = pp[32], chi_c = pc[32];
+    pp -= PD * 32;                                                // row of order n - 1 - PD: the next one the ring takes in
+    pc -= PD * 32;
+    // a zero-weight particle of a dense run adds exact zeros to every sum, even where its coefficients are not finite: not emitted
+    // (unless the per-particle efficiencies are asked for, gm_table_particles: then every particle is evaluated and its rows carry f = 0)
+    // `any`: some weight of the lane is non-zero -- the phase weight may be 0 where a (signed) scalar weight is not ('du' grid)
+    const bool lane_on = act && (any || A.q != nullptr);
+#pragma unroll 4
+    for (; n >= 1; --n, f2 -= 2.0, pp -= 32, pc -= 32) {
+      const double2 ti = crcp(tt);
+      const bool on = n < nmx;
+      const double f1 = 0.5 * f2 + 0.5;                                     // n + 1
+      D.x = on ? fma(f1, zinv.x, -ti.x) : D.x;
+      D.y = on ? fma(f1, zinv.y, -ti.y) : D.y;
+      tt.x = on ? fma(f2, zinv.x, -ti.x) : tt.x;
+      tt.y = on ? fma(f2, zinv.y, -ti.y) : tt.y;
+      const bool emit = lane_on && n <= nm;
+      const double psi_m = rp[0], chi_m = rc[0];                             // order n - 1
+#pragma unroll
+      for (int k = 0; k + 1 < PD; ++k) {
+        rp[k] = rp[k + 1];
+        rc[k] = rc[k + 1];
+      }
+      rp[PD - 1] = *pp;
+      rc[PD - 1] = *pc;
+      const double nox = (0.5 * f2 - 0.5) * xinv;                            // n / x
+      double2 da = cmul(D, minv);                                            // mie_coeffs.py:124
+      da.x += nox;
+      double2 db = cmul(D, mrv);                                             // mie_coeffs.py:125
+      db.x += nox;
+      // a_n = (da psi_n - psi_{n-1}) / (da xi_n - xi_{n-1}),  xi = psi - i chi      (mie_coeffs.py:113-114,127-128)
+      double2 an = cdiv(make_double2(fma(da.x, psi_c, -psi_m), da.y * psi_c),
+                        make_double2(fma(da.x, psi_c, fma(da.y, chi_c, -psi_m)), fma(da.y, psi_c, fma(-da.x, chi_c, chi_m))));
+      double2 bn = cdiv(make_double2(fma(db.x, psi_c, -psi_m), db.y * psi_c),
+                        make_double2(fma(db.x, psi_c, fma(db.y, chi_c, -psi_m)), fma(db.y, psi_c, fma(-db.x, chi_c, chi_m))));
+      psi_c = psi_m;
+      chi_c = chi_m;
+      an.x = emit ? an.x : 0.0;
+      an.y = emit ? an.y : 0.0;
+      bn.x = emit ? bn.x : 0.0;
+      bn.y = emit ? bn.y : 0.0;
+      // efficiencies, mie_props.py:41-65 (orders above a lane's nmax add exact zeros)
+      const double2 nt = __ldg(A.ntab + n);
+      sext += f2 * (an.x + bn.x);
+      ssca += f2 * (an.x * an.x + an.y * an.y + bn.x * bn.x + bn.y * bn.y);
+      const double sg = (n & 1) ? -f2 : f2;
+      qbr += sg * (an.x - bn.x);
+      qbi += sg * (an.y - bn.y);
+      sasy += nt.y * (an.x * a_next.x + an.y * a_next.y + bn.x * b_next.x + bn.y * b_next.y) + nt.x * (an.x * bn.x + an.y * bn.y);
+      a_next = an;
+      b_next = bn;
+      const double f = nt.x * sw;
+      const double2 cp = make_double2((an.x + bn.x) * f, (an.y + bn.y) * f);
+      const double2 cm = make_double2((an.x - bn.x) * f, (an.y - bn.y) * f);
+#ifndef GM_COEFF_NOSTORE
+      double* r = crow + (size_t)(n - 1) * GM_SB;
+#if GM_COEF_STCS
+      __stcs(reinterpret_cast<double2*>(r), cp);
+      __stcs(reinterpret_cast<double2*>(r + 64), cm);
+#else
+      *reinterpret_cast<double2*>(r) = cp;
+      *reinterpret_cast<double2*>(r + 64) = cm;
+#endif
+#endif
+    }
+  }
+#endif
+  // ---- phase 2: orders that emit coefficients (MODE 1 / 2; MODE 0 arrives here with n == 0)
   for (; n >= 1; --n, f2 -= 2.0) {
     if (n < nmx) {
       const double2 ti = crcp(tt);
