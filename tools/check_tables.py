@@ -53,6 +53,7 @@ def check(d, sp):
         B = np.load(os.path.join(G, "gsf_basis.npz"))
         pm = np.array(ncio.Dataset(full, "r").variables["pmom"][:])        # (bin, wavelength, rh, p, m)
         worst = 0.0
+        per_bin = [0.0] * pm.shape[0]
         for li, rhi in cells[::6]:
             for b in range(pm.shape[0]):
                 m_ = pm[b, li, rhi]
@@ -62,9 +63,14 @@ def check(d, sp):
                 R = {"p11": m_[0] @ B["leg"], "p12": m_[1] @ B["d02"], "p22": p22, "p33": a2p3 - p22, "p34": m_[3] @ B["d02"], "p44": m_[5] @ B["leg"]}
                 sc = np.abs(V["p11"][b, li, rhi]).max()
                 for k in R:
-                    worst = max(worst, float(np.max(np.abs(R[k] - V[k][b, li, rhi])) / sc))
+                    e = float(np.max(np.abs(R[k] - V[k][b, li, rhi])) / sc)
+                    worst = max(worst, e)
+                    per_bin[b] = max(per_bin[b], e)
         res["pmom_shape"] = list(pm.shape)
+        # 129 moments represent the phase matrix of particles up to x ~ 50; for the large sea-salt bins (x up to 2513, forward peak ~1e6) the
+        # truncated series cannot reproduce it -- there the number measures the truncation the reference's NSPHER = 129 imposes, not an error
         res["pmom_resynthesis_max_rel_to_p11max"] = worst
+        res["pmom_resynthesis_per_bin"] = per_bin
     return res
 
 
