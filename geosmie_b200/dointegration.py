@@ -434,6 +434,16 @@ def psd_parameters(params, radind, onerh, rh, lam):
     return kind, [[xconv, m[1], m[2], m[3]] for m in modes], rLow, rUp
 
 
+class WavelengthSubset(object):
+    """`cells` argument of BinPlan: every RH cell of the given wavelength indices (what a rank of a multi-GPU build owns)."""
+
+    def __init__(self, li):
+        self.li = np.asarray(li, dtype=np.int64)
+
+    def as_set(self, nr, trivial):
+        return {(int(l), r) for l in self.li for r in range(nr) if not (trivial and r > 0)}
+
+
 class BinPlan(object):
     """Host-side description of one size bin: the grid and, for every (wavelength, RH) cell that must be computed, the
     refractive indices, the size-distribution inputs and the scalars that the reference derives inside its lambda/RH
@@ -467,9 +477,12 @@ class BinPlan(object):
         self.device_psd = device_psd
         self.psd_kind = None
         mr_l, w_l, par_l, meta = [], [], [], []
-        want = None if cells is None else set(cells)
-        if device_psd and want:
-            want |= {(li, 0) for (li, _) in want}      # reff_mass0 comes from the RH-index-0 cell of the same wavelength
+        if isinstance(cells, WavelengthSubset):
+            want = cells if device_psd else cells.as_set(len(rh_used), trivial)      # whole wavelengths: the RH-index-0 cells are included
+        else:
+            want = None if cells is None else set(cells)
+            if device_psd and want:
+                want |= {(li, 0) for (li, _) in want}      # reff_mass0 comes from the RH-index-0 cell of the same wavelength
         if device_psd:
             # the wavelength and the humidity enter the per-cell inputs separately: 61 + 36 evaluations instead of 61 x 36
             self._scan_cells_separable(params, radind, lambarr, rh_used, part_m, water_m, want, trivial)
@@ -530,7 +543,10 @@ class BinPlan(object):
             par[..., 0] = xconv[:, None, None]
             par[..., 1:] = modes[None, :, :, 1:]
         sel = np.ones((nl, len(rlist)), dtype=bool)
-        if want is not None:
+        if isinstance(want, WavelengthSubset):
+            sel[:] = False
+            sel[want.li, :] = True
+        elif want is not None:
             sel[:] = False
             for (li, rhi) in want:
                 if rhi in rlist:
@@ -691,7 +707,7 @@ def fun(partID0, datatype, oppfx, oppclassic, elide=True, write=True, comm=None,
         trivial = params['rhDep']['type'] == 'trivial'
         # Multi-GPU: rank r owns the wavelengths r, r+W, ... with all their RH cells (the RH-index-0 cell that defines
         # mass0 / reff_mass0 stays local), reduces and post-processes them, and only finished rows travel to rank 0.
-        mine = None if world == 1 else [(li, rhi) for li in range(rank, nl, world) for rhi in range(nr) if not (trivial and rhi > 0)]
+        mine = None if world == 1 else WavelengthSubset(np.arange(rank, nl, world))
         plan = BinPlan(params, radind, lambarr, rh_used, part_m, water_m, cells=mine, device_psd=device_psd)
         ncell = len(plan.cells)
         li = np.array([c[0] for c in plan.cells], dtype=np.int64)
@@ -800,11 +816,32 @@ def fun(partID0, datatype, oppfx, oppclassic, elide=True, write=True, comm=None,
             for k, src in dup.items():
                 if src is not None:
                     ret[k] = ret[src]
+            # the rows arrive rank by rank, each rank's in (wavelength, rh) order of its wavelengths r, r + W, ...: one strided block
+            # assignment per rank and variable instead of an element-wise scatter
+            nrr_ = 1 if trivial else nr
+            counts = [len(range(r, nl, world)) * nrr_ for r in range(world)]
+            if sum(counts) == rows.shape[0]:
+                start = 0
+                for r in range(world):
+                    blk = slice(start, start + counts[r])
+                    start += counts[r]
+                    if counts[r] == 0:
+                        continue
+                    for key in keys:
+                        if key not in ret or _kind_of(key) == "nl":
+                            continue
+                        col = np.asarray(ret[key])[blk]
+                        vals[key][radind, r::world, :nrr_] = col.reshape((-1, nrr_) + col.shape[1:])
+                block_done = True
+            else:
+                block_done = False
         if ret is not None:
             for key in keys:
                 if key not in ret:
                     continue                                   # arrived through the peer path
                 col = np.asarray(ret[key])
+                if world > 1 and block_done and _kind_of(key) != "nl":
+                    continue                                   # written rank block by rank block above
                 if _kind_of(key) == "nl":
                     # (bin, rh) variables are overwritten at every wavelength: the last one wins (dointegration.py:1026-1027)
                     last = li == li.max()
