@@ -97,9 +97,35 @@ extern "C" int gm_init(int device, gm_handle_t* out) {
   return GM_OK;
 }
 
+int gm_pool_take(gm_handle_s* h, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return GM_OK;
+  int best = -1;
+  for (int i = 0; i < (int)h->pool.size(); ++i)
+    if (h->pool[i].cap >= bytes && (best < 0 || h->pool[i].cap < h->pool[best].cap)) best = i;      // smallest fit
+  if (best < 0) return b.ensure(bytes);
+  const DevBuf got = h->pool[best];
+  h->pool.erase(h->pool.begin() + best);
+  gm_pool_give(h, b);                   // the too-small buffer, if any
+  b = got;
+  return GM_OK;
+}
+
+void gm_pool_give(gm_handle_s* h, DevBuf& b) {
+  if (!b.p) return;
+  if (b.cap < ((size_t)1 << 20) || h->pool.size() >= 12) {     // small buffers are cheap to re-create; the pool stays bounded
+    b.release();
+    return;
+  }
+  h->pool.push_back(b);
+  b.p = nullptr;
+  b.cap = 0;
+}
+
 extern "C" int gm_destroy(gm_handle_t h) {
   if (!h) return GM_OK;
   cudaSetDevice(h->device);
+  for (auto& b : h->pool) b.release();
+  h->pool.clear();
   for (auto& b : h->ws) b.release();
   for (DevBuf* b : {&h->scratch_coef, &h->scratch_gact, &h->scratch_scal_part, &h->scratch_part, &h->scratch_g_hpart, &h->scratch_g_hsum,
                     &h->scratch_wphase, &h->scratch_wscal, &h->scratch_taskc})
@@ -225,7 +251,7 @@ struct DevGroups {
   double* psi_p = nullptr;
   double* chi_p = nullptr;
   size_t psichi_bytes = 0;
-  int upload(const Groups& G, const double* hx, const int32_t* hnmax, cudaStream_t st) {
+  int upload(const Groups& G, const double* hx, const int32_t* hnmax, cudaStream_t st, gm_handle_s* pool = nullptr) {
     int rc;
     if ((rc = x.ensure(sizeof(double) * G.nx))) return rc;
     if ((rc = xinv.ensure(sizeof(double) * G.nx))) return rc;
@@ -235,7 +261,7 @@ struct DevGroups {
     if ((rc = grow.ensure(sizeof(int) * G.ngroup))) return rc;
     const size_t slack = (size_t)GM_BESSEL_SLACK_ROWS * GM_GROUP;                // doubles of slack around each table (k_coeff's unchecked ring)
     psichi_bytes = sizeof(double) * 2 * ((size_t)G.bessel_len + 2 * slack);
-    if ((rc = psichi.ensure(psichi_bytes))) return rc;                           // psi | chi in ONE allocation
+    if ((rc = pool ? gm_pool_take(pool, psichi, psichi_bytes) : psichi.ensure(psichi_bytes))) return rc;   // psi | chi in ONE allocation
     psi_p = psichi.as<double>() + slack;
     chi_p = psi_p + G.bessel_len + 2 * slack;
     GM_CUDA_TRY(cudaMemcpyAsync(x.p, hx, sizeof(double) * G.nx, cudaMemcpyHostToDevice, st));
@@ -442,8 +468,8 @@ extern "C" int gm_table_create(gm_handle_t h, int nx, const double* x, const int
   t->hnmax.assign(nmax, nmax + nx);
   t->G.build(nx, nmax);
   t->nrows = ((t->G.nmaxmax + GM_KSTEP - 1) / GM_KSTEP) * GM_KSTEP;
-  if ((rc = t->D.upload(t->G, x, nmax, st)) || (rc = t->cost.ensure(sizeof(double) * nang)) ||
-      (rc = t->T.ensure(sizeof(double) * GM_NHALF * (size_t)t->nrows * GM_TROW))) {
+  if ((rc = t->D.upload(t->G, x, nmax, st, h)) || (rc = t->cost.ensure(sizeof(double) * nang)) ||
+      (rc = gm_pool_take(h, t->T, sizeof(double) * GM_NHALF * (size_t)t->nrows * GM_TROW))) {
     delete t;
     return rc;
   }
@@ -472,6 +498,7 @@ extern "C" int gm_table_create(gm_handle_t h, int nx, const double* x, const int
 extern "C" int gm_table_destroy(gm_table_t t) {
   if (!t) return GM_OK;
   cudaSetDevice(t->h->device);
+  for (DevBuf* b : {&t->out_phase, &t->norm_planes, &t->gsf_coef, &t->D.psichi, &t->T}) gm_pool_give(t->h, *b);
   t->D.release();
   for (DevBuf* b : {&t->g_list, &t->g_skip, &t->g_desc, &t->g_items, &t->s_segs, &t->s_big, &t->norm_planes, &t->norm_ang, &t->gsf_coef, &t->gsf_cnorm, &t->c_ab, &t->c_scratch, &t->c_soff, &t->c_aboff, &t->c_ratio, &t->dr, &t->psd_par, &t->psd_frac, &t->T, &t->cost, &t->chunk_start, &t->mz, &t->mrel, &t->out_scal, &t->out_phase, &t->stats, &t->q, &t->s12})
     b->release();
@@ -825,7 +852,7 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
       (rc = t->chunk_start.ensure(sizeof(int) * (nchunk + 1))) || (rc = t->stats.ensure(sizeof(unsigned long long) * 8)))
     return rc;
   if (t->gsf_ng > 0 && !per_particle) {
-    if ((rc = t->gsf_coef.ensure(sizeof(double) * (size_t)ntask * 6 * t->gsf_ng)) || (rc = t->gsf_cnorm.ensure(sizeof(double) * ntask))) return rc;
+    if ((rc = gm_pool_take(t->h, t->gsf_coef, sizeof(double) * (size_t)ntask * 6 * t->gsf_ng)) || (rc = t->gsf_cnorm.ensure(sizeof(double) * ntask))) return rc;
   }
   GM_CUDA_TRY(cudaMemcpyAsync(t->chunk_start.p, cstart.data(), sizeof(int) * (nchunk + 1), cudaMemcpyHostToDevice, st));
   GM_CUDA_TRY(cudaMemsetAsync(t->stats.p, 0, sizeof(unsigned long long) * 8, st));
@@ -1152,7 +1179,7 @@ extern "C" int gm_table_run(gm_table_t t, int ntask, const double* mz, const dou
   const size_t nw = (size_t)ntask * t->nx;
   if ((rc = t->mz.ensure(sizeof(double2) * ntask)) || (rc = t->mrel.ensure(sizeof(double2) * ntask)) ||
       (rc = t->h->scratch_wphase.ensure(sizeof(double) * nw)) || (rc = t->out_scal.ensure(sizeof(double) * (size_t)ntask * nmode * GM_NSCAL)) ||
-      (rc = t->out_phase.ensure(sizeof(double) * (size_t)ntask * 4 * t->nang)))
+      (rc = gm_pool_take(t->h, t->out_phase, sizeof(double) * (size_t)ntask * 4 * t->nang)))
     return rc;
   if (w_scal && (rc = t->h->scratch_wscal.ensure(sizeof(double) * nw * nmode))) return rc;
   GM_CUDA_TRY(cudaMemcpyAsync(t->mz.p, mz, sizeof(double2) * ntask, cudaMemcpyHostToDevice, st));
@@ -1193,7 +1220,7 @@ extern "C" int gm_table_run_coated(gm_table_t t, int ntask, const double* m1, co
   if ((rc = t->mz.ensure(sizeof(double2) * ntask)) || (rc = t->mrel.ensure(sizeof(double2) * ntask)) ||
       (rc = t->c_ratio.ensure(sizeof(double) * ntask)) || (rc = t->h->scratch_wphase.ensure(sizeof(double) * nw)) ||
       (rc = t->out_scal.ensure(sizeof(double) * (size_t)ntask * nmode * GM_NSCAL)) ||
-      (rc = t->out_phase.ensure(sizeof(double) * (size_t)ntask * 4 * t->nang)))
+      (rc = gm_pool_take(t->h, t->out_phase, sizeof(double) * (size_t)ntask * 4 * t->nang)))
     return rc;
   if (w_scal && (rc = t->h->scratch_wscal.ensure(sizeof(double) * nw * nmode))) return rc;
   GM_CUDA_TRY(cudaMemcpyAsync(t->mz.p, m1, sizeof(double2) * ntask, cudaMemcpyHostToDevice, st));
@@ -1266,7 +1293,7 @@ extern "C" int gm_table_run_psd(gm_table_t t, int ntask, const double* mz, const
   for (int i = 0; i < ntask * nmode && !separate; ++i) separate = frac[i] != 1.0;
   if ((rc = t->mz.ensure(sizeof(double2) * ntask)) || (rc = t->mrel.ensure(sizeof(double2) * ntask)) ||
       (rc = t->h->scratch_wphase.ensure(sizeof(double) * nw)) || (rc = t->out_scal.ensure(sizeof(double) * (size_t)ntask * nmode * GM_NSCAL)) ||
-      (rc = t->out_phase.ensure(sizeof(double) * (size_t)ntask * 4 * t->nang)) ||
+      (rc = gm_pool_take(t->h, t->out_phase, sizeof(double) * (size_t)ntask * 4 * t->nang)) ||
       (rc = t->psd_par.ensure(sizeof(double) * (size_t)ntask * nmode * GM_PSD_NPAR)) ||
       (rc = t->psd_frac.ensure(sizeof(double) * (size_t)ntask * nmode)))
     return rc;
@@ -1314,7 +1341,7 @@ static int normalize_on_device(gm_table_t t, int ntask, const double* theta_rad,
   cudaStream_t st = h->stream;
   int rc;
   const size_t plane = (size_t)ntask * t->nang;
-  if ((rc = t->norm_planes.ensure(sizeof(double) * ((want_planes ? 4 * plane : 0) + 4 * (size_t)ntask))) || (rc = t->norm_ang.ensure(sizeof(double) * 2 * t->nang)))
+  if ((rc = gm_pool_take(t->h, t->norm_planes, sizeof(double) * ((want_planes ? 4 * plane : 0) + 4 * (size_t)ntask))) || (rc = t->norm_ang.ensure(sizeof(double) * 2 * t->nang)))
     return rc;
   double* d_ang = t->norm_ang.as<double>();
   GM_CUDA_TRY(cudaMemcpyAsync(d_ang, theta_rad, sizeof(double) * t->nang, cudaMemcpyHostToDevice, st));
@@ -1370,7 +1397,7 @@ extern "C" int gm_table_particles(gm_table_t t, int ntask, const double* mz, con
   GM_CUDA_TRY(cudaMemcpyAsync(t->mz.p, mz, sizeof(double2) * ntask, cudaMemcpyHostToDevice, st));
   GM_CUDA_TRY(cudaMemcpyAsync(t->mrel.p, mrel, sizeof(double2) * ntask, cudaMemcpyHostToDevice, st));
   GM_CUDA_TRY(cudaMemsetAsync(t->h->scratch_wphase.p, 0, sizeof(double) * np, st));
-  if ((rc = t->out_scal.ensure(sizeof(double) * (size_t)ntask * GM_NSCAL)) || (rc = t->out_phase.ensure(sizeof(double) * (size_t)ntask * 4 * t->nang)))
+  if ((rc = t->out_scal.ensure(sizeof(double) * (size_t)ntask * GM_NSCAL)) || (rc = gm_pool_take(t->h, t->out_phase, sizeof(double) * (size_t)ntask * 4 * t->nang)))
     return rc;
   rc = table_run_core(t, ntask, t->mz.as<double>(), t->mrel.as<double>(), 1, t->h->scratch_wphase.as<double>(), nullptr, 0,
                       t->out_scal.as<double>(), t->out_phase.as<double>(), t->q.as<double>(), s12 ? t->s12.as<double>() : nullptr,

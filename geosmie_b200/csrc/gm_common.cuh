@@ -68,6 +68,10 @@ struct gm_handle_s {
   size_t coef_budget_bytes = (size_t)4 << 30;  // coefficient staging buffer per gm_table_run batch (optics_SU dense: 2.9 GB = one batch)
   // per-run scratch of gm_table_run* (coefficient stream, partial sums, weights): grow-only and shared by all tables of the
   // handle, so that building one table per size bin does not pay a multi-GB cudaMalloc / cudaFree per bin
+  // buffers handed back by destroyed tables (phase sums, normalised planes, GSF moments: up to ~1 GB each on fine spectral grids):
+  // a table build walks through its size bins with one table after the other, and cudaFree + cudaMalloc of these buffers was 0.34 s of
+  // the 2.3 s optics_SS 2048-wavelength build
+  std::vector<DevBuf> pool;
   DevBuf scratch_coef, scratch_gact, scratch_scal_part, scratch_part, scratch_g_hpart, scratch_g_hsum, scratch_wphase, scratch_wscal, scratch_taskc;
   // GSF constants (Gauss nodes, interpolation brackets, generalized spherical functions) cached per angle grid
   DevBuf gsf_nodes, gsf_table, gsf_alt, gsf_raw;
@@ -82,6 +86,10 @@ struct gm_handle_s {
   cudaEvent_t peer_marks[4] = {nullptr, nullptr, nullptr, nullptr};   // gm_peer_mark / gm_peer_wait
   bool peer_pending = false;
 };
+
+// take a buffer of at least `bytes` for `b` from the handle's pool (smallest fit) or allocate it; give one back (bounded pool)
+int gm_pool_take(gm_handle_s* h, DevBuf& b, size_t bytes);
+void gm_pool_give(gm_handle_s* h, DevBuf& b);
 
 // GSF expansion of gm_table_run's phase layout on device pointers (gm_gsf.cu); asynchronous on the handle's stream
 int gm_gsf_phase4_async(gm_handle_s* h, int ncell, int nang, const double* h_ang_deg, const double* d_P4, int ng, double* d_coef,
