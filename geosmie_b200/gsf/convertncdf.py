@@ -118,9 +118,7 @@ def processFileRaw(infile, outdir, whichproc, rhop0, mode, ice, quantize=True):
     if mode == 'legendre':
         fn = os.path.basename(infile)
         outfile = os.path.join(outdir, fn.replace('nomom.', ''))
-        if os.path.abspath(outfile) != os.path.abspath(infile):
-            shutil.copyfile(infile, outfile)
-        nc = ncio.Dataset(outfile, 'r+')
+        nc = ncio.open_copy(infile, outfile)
         print('mode %s' % mode)
         process_legendre(nc, quantize=quantize)
         nc.close()
@@ -128,15 +126,14 @@ def processFileRaw(infile, outdir, whichproc, rhop0, mode, ice, quantize=True):
         return outfile
     fn = os.path.basename(infile)
     outfile = os.path.join(outdir, fn.replace('nomom.', ''))
-    shutil.copyfile(infile, outfile)
-    nc = ncio.Dataset(outfile, 'r+')
+    nc = ncio.open_copy(infile, outfile)      # copy of the .nomom file that gains `pmom` (convertncdf.py:331-332)
     oppclassic = 'wavelength' not in nc.variables
     if oppclassic:
         print("Operating on a legacy file")
     print('mode %s' % mode)
     createVariablesPyGeosMie(nc, NUM_EXPAND, oppclassic)
     ang = np.array(nc.variables['ang'][:])
-    elements = {k: np.array(nc.variables[k][:]) for k in MISH_KEYS}
+    elements = {k: np.asarray(nc.variables[k][:]) for k in MISH_KEYS}
     nc.variables['pmom'][:] = expand_table(ang, elements, oppclassic, quantize=quantize)
     nc.close()
     print("%s done" % fn)
