@@ -112,8 +112,10 @@ int gm_pool_take(gm_handle_s* h, DevBuf& b, size_t bytes) {
 
 void gm_pool_give(gm_handle_s* h, DevBuf& b) {
   if (!b.p) return;
-  if (b.cap < ((size_t)1 << 20) || h->pool.size() >= 12) {     // small buffers are cheap to re-create; the pool stays bounded
-    b.release();
+  size_t held = 0;
+  for (const auto& q : h->pool) held += q.cap;
+  if (b.cap < ((size_t)1 << 20) || h->pool.size() >= 12 || held + b.cap > ((size_t)8 << 30)) {
+    b.release();                        // small buffers are cheap to re-create; the pool stays bounded (12 buffers, 8 GB)
     return;
   }
   h->pool.push_back(b);

@@ -24,7 +24,7 @@ timeout 300 python tools/profile_fine.py ss 2048 > gpurun_out/f_profile_fine.txt
 echo "== ncu launch lists of bench.py"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_launches_bench_su.csv \
    python bench.py --workloads su --steps 2 --warmup 3 --no-lut --no-cpu-baseline > gpurun_out/f_ncu_su.log 2>&1; wc -l gpurun_out/r02_launches_bench_su.csv
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/r02_launches_bench_ss.csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file gpurun_out/r02_launches_bench_ss.csv \
    python bench.py --workloads ss --steps 2 --warmup 3 --no-lut --no-cpu-baseline > gpurun_out/f_ncu_ss.log 2>&1; wc -l gpurun_out/r02_launches_bench_ss.csv
 echo "== DRAM bytes"
 timeout 400 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/launches_su.csv \
