@@ -89,6 +89,7 @@ def flop_model(nmax, nmx_sum, ncell_factor=1):
     small = gm <= 8
     pg = np.repeat(in_gram, 32)[:len(nm)]
     ps = np.repeat(small, 32)[:len(nm)]
+    ngram = 8.0 * float(tg[in_gram].max()) if in_gram.any() else 0.0
     dm = np.where(gm <= 4, 32.0, np.where(tg <= 4, 64.0 * tg * tg, 16.0 * 12.0 * tg * np.floor((tg + 2) / 3)))
     return {"contract": snm * 8.0 * NANG + npart * 16.0 * NANG,
             "contract_direct": (float(nm[~pg].sum()) * 8.0 * NANG + float((~pg).sum()) * 16.0 * NANG) * ncell_factor,
@@ -100,7 +101,9 @@ def flop_model(nmax, nmx_sum, ncell_factor=1):
             "gram_exec_big": 512.0 * float(dm[in_gram & ~small].sum()) * ncell_factor,
             "coeff": 14.0 * nmx_sum + 94.0 * snm,
             "coeff_small": 94.0 * float(nm[ps].sum()) * ncell_factor,      # + 14 nmx of those particles (not split out by the kernel stats)
-            "eval": 8.0 * NANG * float(nm[pg].max() if pg.any() else 0.0) ** 2 * ncell_factor}
+            # k_gram_eval + k_gram_interp: the four quadratic forms at the 2 N + 1 Chebyshev nodes (N = 8 x largest Gram class), then the
+            # barycentric interpolation of the four degree-2N polynomials to the table's angles
+            "eval": ((8.0 * (2 * ngram + 1) * ngram ** 2 + 8.0 * NANG * (2 * ngram + 1)) if pg.any() else 0.0) * ncell_factor}
 
 
 # ----------------------------------------------------------------------------------------------- clocks
@@ -602,7 +605,7 @@ def main():
                         "flop": fl["coeff"] - fl["coeff_small"]},
             "k_gram_sum+k_gram_eval": {"bound": "tensor", "ms": kms.get("k_gram_sum_eval", 0.0), "achieved": tf(fl["eval"], kms.get("k_gram_sum_eval", 0.0)),
                                        "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "flop": fl["eval"],
-                                       "note": "4 quadratic forms of size max(nmax of the Gram groups) at 371 angles per cell"},
+                                       "note": "4 quadratic forms of size N = 8 x (largest Gram class) at the 2 N + 1 Chebyshev nodes per cell + interpolation of the four polynomials to the 371 angles"},
             "k_finalize": {"bound": "hbm", "ms": kms.get("k_finalize", 0.0)},
         }
         for name, k in kernels.items():

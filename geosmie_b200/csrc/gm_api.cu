@@ -130,7 +130,7 @@ extern "C" int gm_destroy(gm_handle_t h) {
   h->pool.clear();
   for (auto& b : h->ws) b.release();
   for (DevBuf* b : {&h->scratch_coef, &h->scratch_gact, &h->scratch_scal_part, &h->scratch_part, &h->scratch_g_hpart, &h->scratch_g_hsum,
-                    &h->scratch_wphase, &h->scratch_wscal, &h->scratch_taskc})
+                    &h->scratch_wphase, &h->scratch_wscal, &h->scratch_taskc, &h->scratch_nodepart})
     b->release();
   h->gsf_nodes.release();
   h->gsf_table.release();
@@ -425,6 +425,8 @@ struct gm_table_s {
   DevBuf T, cost, dr, psd_par, psd_frac;
   DevBuf g_list, g_skip, g_desc, g_items;   // Gram path (gm_gram.cuh)
   DevBuf norm_planes, norm_ang;              // gm_table_fetch_normalized
+  DevBuf T2, W;                              // Gram evaluation through Chebyshev nodes: p/q table at the nodes, interpolation matrix
+  int nnode = 0;
   DevBuf s_segs, s_big;                      // fused small-class path (gm_small.cuh): work-item segments, groups left to k_coeff
   DevBuf c_ab, c_scratch, c_soff, c_aboff, c_ratio;   // coated-sphere table path
   // fused GSF stage (gm_table_set_gsf): moments of every finished batch are expanded and downloaded behind the kernels
@@ -492,7 +494,53 @@ extern "C" int gm_table_create(gm_handle_t h, int nx, const double* x, const int
   GM_LAUNCH_CHECK(h);
   k_xinv<<<(nx + 127) / 128, 128, 0, st>>>(nx, t->D.x.as<double>(), t->D.xinv.as<double>());
   GM_LAUNCH_CHECK(h);
+  std::vector<double> hW;
+  DevBuf nodes_d;
+  if (!t->G.glist.empty() && getenv("GEOSMIE_EVAL_DIRECT") == nullptr) {
+    // Chebyshev nodes u_j = cos(pi j / (M - 1)), M = 2 N + 1 with N = 8 x (largest Gram class): the quadratic forms of k_gram_eval are
+    // polynomials of degree <= 2 N in u; W[j][a] = barycentric weight of node j for the table angle a (second-kind weights (-1)^j, halved
+    // at the ends; a table angle that coincides with a node takes that node's value)
+    const int N = 8 * t->G.gram_tgmax;
+    const int M = 2 * N + 1;
+    if (M <= GM_HALF_ANG && M < nang) {
+      const double pi = 3.14159265358979323846;
+      std::vector<double> un(M);
+      for (int j = 0; j < M; ++j) un[j] = cos(pi * j / (M - 1));
+      un[0] = 1.0;
+      un[M - 1] = -1.0;
+      hW.assign((size_t)M * GM_NANG_PAD, 0.0);
+      for (int a = 0; a < nang; ++a) {
+        const double ua = cos_theta[a];
+        int hit = -1;
+        for (int j = 0; j < M; ++j)
+          if (ua == un[j]) hit = j;
+        if (hit >= 0) {
+          hW[(size_t)hit * GM_NANG_PAD + a] = 1.0;
+          continue;
+        }
+        double sum = 0.0;
+        for (int j = 0; j < M; ++j) {
+          const double wj = ((j & 1) ? -1.0 : 1.0) * ((j == 0 || j == M - 1) ? 0.5 : 1.0) / (ua - un[j]);
+          hW[(size_t)j * GM_NANG_PAD + a] = wj;
+          sum += wj;
+        }
+        for (int j = 0; j < M; ++j) hW[(size_t)j * GM_NANG_PAD + a] /= sum;
+      }
+      if ((rc = t->T2.ensure(sizeof(double) * GM_NHALF * (size_t)t->nrows * GM_TROW)) || (rc = t->W.ensure(sizeof(double) * hW.size())) ||
+          (rc = nodes_d.ensure(sizeof(double) * M))) {
+        delete t;
+        return rc;
+      }
+      GM_CUDA_TRY(cudaMemcpyAsync(nodes_d.p, un.data(), sizeof(double) * M, cudaMemcpyHostToDevice, st));
+      GM_CUDA_TRY(cudaMemcpyAsync(t->W.p, hW.data(), sizeof(double) * hW.size(), cudaMemcpyHostToDevice, st));
+      GM_CUDA_TRY(cudaMemsetAsync(t->T2.p, 0, sizeof(double) * GM_NHALF * (size_t)t->nrows * GM_TROW, st));
+      k_pt_table<<<(GM_NANG_PAD + 127) / 128, 128, 0, st>>>(M, nodes_d.as<double>(), t->nrows, t->T2.as<double>());
+      GM_LAUNCH_CHECK(h);
+      t->nnode = M;
+    }
+  }
   GM_CUDA_TRY(cudaStreamSynchronize(st));
+  nodes_d.release();
   *out = t;
   return GM_OK;
 }
@@ -502,7 +550,7 @@ extern "C" int gm_table_destroy(gm_table_t t) {
   cudaSetDevice(t->h->device);
   for (DevBuf* b : {&t->out_phase, &t->norm_planes, &t->gsf_coef, &t->D.psichi, &t->T}) gm_pool_give(t->h, *b);
   t->D.release();
-  for (DevBuf* b : {&t->g_list, &t->g_skip, &t->g_desc, &t->g_items, &t->s_segs, &t->s_big, &t->norm_planes, &t->norm_ang, &t->gsf_coef, &t->gsf_cnorm, &t->c_ab, &t->c_scratch, &t->c_soff, &t->c_aboff, &t->c_ratio, &t->dr, &t->psd_par, &t->psd_frac, &t->T, &t->cost, &t->chunk_start, &t->mz, &t->mrel, &t->out_scal, &t->out_phase, &t->stats, &t->q, &t->s12})
+  for (DevBuf* b : {&t->g_list, &t->g_skip, &t->g_desc, &t->g_items, &t->s_segs, &t->s_big, &t->norm_planes, &t->norm_ang, &t->T2, &t->W, &t->gsf_coef, &t->gsf_cnorm, &t->c_ab, &t->c_scratch, &t->c_soff, &t->c_aboff, &t->c_ratio, &t->dr, &t->psd_par, &t->psd_frac, &t->T, &t->cost, &t->chunk_start, &t->mz, &t->mrel, &t->out_scal, &t->out_phase, &t->stats, &t->q, &t->s12})
     b->release();
   for (auto& e : t->evpool) cudaEventDestroy(e);
   for (auto& e : t->io_events) cudaEventDestroy(e);
@@ -851,6 +899,7 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
   if ((rc = t->h->scratch_coef.ensure(per_task_bytes * tb)) || (rc = t->h->scratch_gact.ensure((size_t)tb * G.ngroup)) ||
       (rc = t->h->scratch_scal_part.ensure(sizeof(double) * (size_t)tb * nmode * G.ngroup * GM_NSCAL)) ||
       (rc = t->h->scratch_part.ensure(sizeof(double) * (size_t)tb * nchunk_total * 4 * GM_NANG_PAD)) ||
+      (rc = (use_gram && t->nnode > 0) ? t->h->scratch_nodepart.ensure(sizeof(double) * (size_t)tb * 4 * GM_NANG_PAD) : GM_OK) ||
       (rc = t->chunk_start.ensure(sizeof(int) * (nchunk + 1))) || (rc = t->stats.ensure(sizeof(unsigned long long) * 8)))
     return rc;
   if (t->gsf_ng > 0 && !per_particle) {
@@ -1081,10 +1130,20 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
       EA.part = t->h->scratch_part.as<double>();
       EA.nchunk = nchunk_total;
       EA.chunk = nchunk;
+      int eblocks = 4;                                     // blocks of 96 angles
+      if (t->nnode > 0) {
+        // evaluate at the 2 N + 1 Chebyshev nodes only; k_gram_interp carries the four polynomials to the table's angles
+        eblocks = (t->nnode + 95) / 96;
+        EA.T = t->T2.as<double>();
+        EA.part = t->h->scratch_nodepart.as<double>();
+        EA.nchunk = 1;
+        EA.chunk = 0;
+        EA.tasks_per_cta = std::max(1, (nt * eblocks + GM_EVAL_CTAS_PER_SM * h->sm_count - 1) / (GM_EVAL_CTAS_PER_SM * h->sm_count));
+      }
       if ((rc = ev_mark(t, 4))) return rc;
       k_gram_sum<<<dim3((2 * N * N + 255) / 256, nt), 256, 0, st>>>(SA);
       GM_LAUNCH_CHECK(h);
-      const dim3 egrid(4, (nt + EA.tasks_per_cta - 1) / EA.tasks_per_cta);
+      const dim3 egrid(eblocks, (nt + EA.tasks_per_cta - 1) / EA.tasks_per_cta);
       switch (EA.ntile) {
         case 1: k_gram_eval<1><<<egrid, GM_GRAM_EVAL_THREADS, EA.nbuf * hbytes, st>>>(EA); break;
         case 2: k_gram_eval<2><<<egrid, GM_GRAM_EVAL_THREADS, EA.nbuf * hbytes, st>>>(EA); break;
@@ -1096,6 +1155,11 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
         default: k_gram_eval<8><<<egrid, GM_GRAM_EVAL_THREADS, EA.nbuf * hbytes, st>>>(EA); break;
       }
       GM_LAUNCH_CHECK(h);
+      if (t->nnode > 0) {
+        k_gram_interp<<<nt, GM_NANG_PAD, 0, st>>>(t->nang, t->nnode, t->W.as<double>(), t->h->scratch_nodepart.as<double>(),
+                                                  t->h->scratch_part.as<double>(), nchunk_total, nchunk);
+        GM_LAUNCH_CHECK(h);
+      }
       if ((rc = ev_mark(t, 4))) return rc;
     }
     if (!per_particle) {

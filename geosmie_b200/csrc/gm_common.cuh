@@ -72,7 +72,7 @@ struct gm_handle_s {
   // a table build walks through its size bins with one table after the other, and cudaFree + cudaMalloc of these buffers was 0.34 s of
   // the 2.3 s optics_SS 2048-wavelength build
   std::vector<DevBuf> pool;
-  DevBuf scratch_coef, scratch_gact, scratch_scal_part, scratch_part, scratch_g_hpart, scratch_g_hsum, scratch_wphase, scratch_wscal, scratch_taskc;
+  DevBuf scratch_coef, scratch_gact, scratch_scal_part, scratch_part, scratch_g_hpart, scratch_g_hsum, scratch_wphase, scratch_wscal, scratch_taskc, scratch_nodepart;
   // GSF constants (Gauss nodes, interpolation brackets, generalized spherical functions) cached per angle grid
   DevBuf gsf_nodes, gsf_table, gsf_alt, gsf_raw;
   std::vector<double> gsf_key;

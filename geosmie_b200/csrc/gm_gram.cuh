@@ -459,3 +459,27 @@ __global__ void __launch_bounds__(GM_GRAM_EVAL_THREADS, 1) k_gram_eval(GramEvalA
   }
 }
 
+
+// ================================================================================================ k_gram_interp
+// The four quadratic forms are POLYNOMIALS of degree <= 2 N in u = cos(theta) (p_n = pi_n + tau_n and q_n = pi_n - tau_n are polynomials
+// of degree n), so k_gram_eval evaluates them at M = 2 N + 1 Chebyshev nodes only (81 instead of 371 angles for optics_SU) and this kernel
+// carries them to the table's angles with the barycentric interpolation matrix W [M][GM_NANG_PAD] built on the host (exact for these
+// polynomials; Lebesgue constant 3.7: numpy prototype 9e-15 of max |S+|^2).  grid = ntask, block = GM_NANG_PAD; fixed summation order.
+__global__ void __launch_bounds__(GM_NANG_PAD) k_gram_interp(int nang, int M, const double* __restrict__ W, const double* __restrict__ node,
+                                                            double* __restrict__ part, int nchunk, int chunk) {
+  __shared__ double nv[4][GM_HALF_ANG];
+  const int task = blockIdx.x, a = threadIdx.x;
+  const double* src = node + (size_t)task * 4 * GM_NANG_PAD;
+  for (int e = a; e < 4 * M; e += GM_NANG_PAD) nv[e / M][e % M] = src[(size_t)(e / M) * GM_NANG_PAD + e % M];
+  __syncthreads();
+  if (a >= nang) return;
+  double s[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int j = 0; j < M; ++j) {
+    const double w = W[(size_t)j * GM_NANG_PAD + a];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) s[b] = fma(w, nv[b][j], s[b]);
+  }
+  double* o = part + (((size_t)task * nchunk + chunk) * 4) * GM_NANG_PAD + a;
+#pragma unroll
+  for (int b = 0; b < 4; ++b) o[(size_t)b * GM_NANG_PAD] = s[b];
+}
