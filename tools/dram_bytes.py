@@ -3,7 +3,7 @@
     python tools/dram_bytes.py gpurun_out/launches_su.csv su 2196 [gpurun_out/launches_ss.csv ss 10980] > profiles/r02_dram_bytes.json"""
 import csv, json, re, sys
 
-KEYS = [("k_coeff", "k_coeff"), ("k_small", "k_small"), ("k_task_prep", "k_small"), ("k_gram_sum", "k_gram_sum_eval"), ("k_gram_eval", "k_gram_sum_eval"),
+KEYS = [("k_coeff", "k_coeff"), ("k_small", "k_small"), ("k_task_prep", "k_small"), ("k_gram_sum", "k_gram_sum_eval"), ("k_gram_eval", "k_gram_sum_eval"), ("k_gram_interp", "k_gram_sum_eval"),
         ("k_gram", "k_gram"), ("k_contract", "k_contract"), ("k_finalize", "k_finalize"), ("k_gsf", "k_gsf"), ("k_psd", "k_psd"),
         ("k_bessel", "k_bessel"), ("k_pt_table", "k_pt_table"), ("k_xinv", "k_xinv")]
 NAMES = {"su": "optics_SU", "ss": "optics_SS"}
