@@ -312,14 +312,19 @@ __global__ void __launch_bounds__(256) k_gram_sum(GramSumArgs A) {
     const int Nd = d.tg ? 8 * d.tg : 4;   // class 0 (stacked, nmax <= 4) writes 4 x 4 blocks
     if (n < Nd && c < Nd) {
       const double2* p = reinterpret_cast<const double2*>(hp + d.hoff + ((size_t)b * Nd + n) * Nd + c);
-      const size_t stride = (size_t)2 * Nd * Nd;   // 4 Nd^2 doubles per team
-      double2 v[12];
-#pragma unroll
-      for (int t = 0; t < 12; ++t) v[t] = t < d.nteam ? p[t * stride] : make_double2(0.0, 0.0);
-#pragma unroll
-      for (int t = 0; t < 12; ++t) {
-        s.x += v[t].x;
-        s.y += v[t].y;
+      const size_t stride = (size_t)2 * Nd * Nd;   // 4 Nd^2 doubles per slot
+      // slots in order (deterministic); k_gram's descriptors have ONE slot since a team owns whole tasks, k_small's up to 12: the loads of
+      // four slots are issued together
+      int t = 0;
+      for (; t + 4 <= d.nteam; t += 4) {
+        const double2 v0 = p[t * stride], v1 = p[(t + 1) * stride], v2 = p[(t + 2) * stride], v3 = p[(t + 3) * stride];
+        s.x = (((s.x + v0.x) + v1.x) + v2.x) + v3.x;
+        s.y = (((s.y + v0.y) + v1.y) + v2.y) + v3.y;
+      }
+      for (; t < d.nteam; ++t) {
+        const double2 v = p[t * stride];
+        s.x += v.x;
+        s.y += v.y;
       }
     }
   }
@@ -467,17 +472,21 @@ __global__ void __launch_bounds__(GM_GRAM_EVAL_THREADS, 1) k_gram_eval(GramEvalA
 // polynomials; Lebesgue constant 3.7: numpy prototype 9e-15 of max |S+|^2).  grid = ntask, block = GM_NANG_PAD; fixed summation order.
 __global__ void __launch_bounds__(GM_NANG_PAD) k_gram_interp(int nang, int M, const double* __restrict__ W, const double* __restrict__ node,
                                                             double* __restrict__ part, int nchunk, int chunk) {
-  __shared__ double nv[4][GM_HALF_ANG];
+  __shared__ __align__(16) double nv[GM_HALF_ANG][4];      // [node][form]: one thread reads its four node values with two 16-byte loads
   const int task = blockIdx.x, a = threadIdx.x;
   const double* src = node + (size_t)task * 4 * GM_NANG_PAD;
-  for (int e = a; e < 4 * M; e += GM_NANG_PAD) nv[e / M][e % M] = src[(size_t)(e / M) * GM_NANG_PAD + e % M];
+  for (int e = a; e < 4 * M; e += GM_NANG_PAD) nv[e % M][e / M] = src[(size_t)(e / M) * GM_NANG_PAD + e % M];
   __syncthreads();
   if (a >= nang) return;
   double s[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 4
   for (int j = 0; j < M; ++j) {
     const double w = W[(size_t)j * GM_NANG_PAD + a];
-#pragma unroll
-    for (int b = 0; b < 4; ++b) s[b] = fma(w, nv[b][j], s[b]);
+    const double2 v01 = *reinterpret_cast<const double2*>(&nv[j][0]), v23 = *reinterpret_cast<const double2*>(&nv[j][2]);
+    s[0] = fma(w, v01.x, s[0]);
+    s[1] = fma(w, v01.y, s[1]);
+    s[2] = fma(w, v23.x, s[2]);
+    s[3] = fma(w, v23.y, s[3]);
   }
   double* o = part + (((size_t)task * nchunk + chunk) * 4) * GM_NANG_PAD + a;
 #pragma unroll
