@@ -23,6 +23,11 @@
 #pragma once
 #include "gm_mie_kernels.cuh"
 
+#ifndef GM_GRAM_SYMMETRIC
+#define GM_GRAM_SYMMETRIC 0   // bit mask (1: 2-warp teams, 2: 4-warp teams, 4: 12-warp teams; 8: skip the ragged duplicate tiles): H1 = X+ X+^T, H2 = X- X-^T from the tiles on and above the diagonal only (mirrored at the flush; -20 % DMMAs on
+                              // optics_SU).  Measured SLOWER (k_gram 0.871 -> 0.989 ms: the skipped tiles leave the H1/H2 warps of a team idle while the
+                              // H3/H4 warps set its pace, and the predicated tile loops schedule worse), so it stays off.
+#endif
 constexpr int GM_GRAM_MAX_TG = 8;                                    // groups with max nmax <= 64 take the Gram path
 constexpr int GM_GRAM_THREADS = (GM_CONTRACT_WARPS + 1) * 32;        // 12 consumer warps + 1 producer warp
 constexpr int GM_GRAM_MAX_SLOTS = 48;
@@ -82,6 +87,7 @@ __device__ __forceinline__ void gram_cta(const GramArgs& A, const GramItem it, c
   using C = GramCfg<TG>;
   constexpr int S = C::S, NTEAM = C::NTEAM, DEPTH = C::DEPTH, R = C::R, SLOT_DBL = C::SLOT_DBL, NI = C::NI, NJ = C::NJ, NJOB = C::NJOB;
   constexpr int N = C::ND;
+  constexpr bool GM_GRAM_SYM_S = (GM_GRAM_SYMMETRIC & (S == 2 ? 1 : S == 4 ? 2 : S == 12 ? 4 : 0)) != 0;   // mirrored tiles in this class
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int lk = lane & 3, lr = lane >> 2;
 
@@ -196,6 +202,7 @@ __device__ __forceinline__ void gram_cta(const GramArgs& A, const GramItem it, c
           for (int i = 0; i < NI; ++i)
 #pragma unroll
             for (int j = 0; j < NI; ++j) {
+              if ((GM_GRAM_SYMMETRIC & 1) && r == 0 && j < i) continue;      // H1, H2 are symmetric: tile (i, j) = tile (j, i)^T
               dmma884(acc[0][i][j][0], acc[0][i][j][1], fp[i], b0[j]);
               dmma884(acc[1][i][j][0], acc[1][i][j][1], a1[i], fm[j]);
             }
@@ -203,7 +210,8 @@ __device__ __forceinline__ void gram_cta(const GramArgs& A, const GramItem it, c
       } else {
         const double* sa = st + aoff;
         const double* sb = st + boff;
-        const int jlast = (S == 12 && j0 + NJ > TG) ? TG - 1 - j0 : NJ - 1;   // ragged last third: recompute the last column tile (not stored)
+        const int jlast = (S == 12 && j0 + NJ > TG) ? TG - 1 - j0 : NJ - 1;   // ragged last third: its column tiles beyond TG do not exist
+        const bool sym = (GM_GRAM_SYMMETRIC & (S == 12 ? 4 : 2)) && blk < 2;                       // H1, H2: only the tiles on and above the diagonal
 #pragma unroll 2
         for (int ks = 0; ks < 16; ++ks) {
           double b[NJ];
@@ -218,7 +226,10 @@ __device__ __forceinline__ void gram_cta(const GramArgs& A, const GramItem it, c
             const double at = sgn * __shfl_xor_sync(0xffffffffu, a, 1);
             a = tilde ? at : a;
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) dmma884(acc[0][i][j][0], acc[0][i][j][1], a, b[j]);
+            for (int j = 0; j < NJ; ++j) {
+              if (((GM_GRAM_SYMMETRIC & 8) && j > jlast) || (sym && i > j0 + j)) continue;
+              dmma884(acc[0][i][j][0], acc[0][i][j][1], a, b[j]);
+            }
           }
         }
       }
@@ -247,9 +258,15 @@ __device__ __forceinline__ void gram_cta(const GramArgs& A, const GramItem it, c
 #pragma unroll
           for (int j = 0; j < NJ; ++j) {
             const int jc = j0 + j;
-            if (jc < TG)
-              *reinterpret_cast<double2*>(hp + ((size_t)b * N + 8 * i + lr) * N + 8 * jc + 2 * lk) =
-                  make_double2(acc[q][i][j][0], acc[q][i][j][1]);
+            if (jc < TG) {
+              if (!(GM_GRAM_SYM_S && b < 2 && i > jc))
+                *reinterpret_cast<double2*>(hp + ((size_t)b * N + 8 * i + lr) * N + 8 * jc + 2 * lk) =
+                    make_double2(acc[q][i][j][0], acc[q][i][j][1]);
+              if (GM_GRAM_SYM_S && b < 2 && i < jc) {       // the mirror tile (same products, same order: bit-identical)
+                hp[((size_t)b * N + 8 * jc + 2 * lk) * N + 8 * i + lr] = acc[q][i][j][0];
+                hp[((size_t)b * N + 8 * jc + 2 * lk + 1) * N + 8 * i + lr] = acc[q][i][j][1];
+              }
+            }
             acc[q][i][j][0] = acc[q][i][j][1] = 0.0;
           }
       }
