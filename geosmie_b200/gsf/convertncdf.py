@@ -34,17 +34,26 @@ def createVariablesPyGeosMie(ncdf, numExpand, oppclassic):
 def expand_table(ang, elements, oppclassic, quantize=True, handle=None):
     """elements: {key: array} for the six MISH_KEYS in file layout -> pmom array in file layout.
     quantize=True rounds to 10 decimals like the Fortran F17.10 text round trip (spher_expan.f:96,104)."""
-    a = [np.asarray(elements[k], dtype=float) for k in MISH_KEYS]
+    first = elements[MISH_KEYS[0]]
     if oppclassic:                       # (radius, rh, lambda, ang) -> (radius, lambda, rh, ang)
-        a = [v.transpose(0, 2, 1, 3) for v in a]
-    nb, nl, nr, na = a[0].shape
-    F = np.stack(a, axis=3).reshape(nb * nl * nr, 6, na)
+        nb, nr, nl, na = first.shape
+    else:
+        nb, nl, nr, na = first.shape
+    # the six elements of a cell side by side: every file variable is decoded straight into its column of F (one pass each)
+    F = np.empty((nb, nl, nr, 6, na))
+    for k, key in enumerate(MISH_KEYS):
+        dst = F[:, :, :, k, :]
+        if oppclassic:
+            dst = dst.transpose(0, 2, 1, 3)
+        v = elements[key]
+        if hasattr(v, "read_into"):
+            v.read_into(dst)
+        else:
+            np.copyto(dst, np.asarray(v[:], dtype=float))
     h = handle or _lib.Handle.get()
-    coef, _ = h.gsf_expand(ang, F, NUM_EXPAND, quantize10=quantize)
-    pm = np.zeros((nb, nl, nr, 6, NUM_EXPAND))
-    coef = coef.reshape(nb, nl, nr, 6, NUM_EXPAND)
-    for ii, npol in enumerate(NPOL_OF_COLUMN):
-        pm[:, :, :, npol, :] = coef[:, :, :, ii, :]
+    coef, _ = h.gsf_expand(ang, F.reshape(nb * nl * nr, 6, na), NUM_EXPAND, quantize10=quantize)
+    inv = np.argsort(NPOL_OF_COLUMN)     # file order (nPol) <- Mishchenko's column order
+    pm = np.take(coef.reshape(nb, nl, nr, 6, NUM_EXPAND), inv, axis=3)
     if oppclassic:                       # ('nPol','nMom','radius','rh','lambda')
         pm = pm.transpose(3, 4, 0, 2, 1)
     return pm
@@ -133,7 +142,7 @@ def processFileRaw(infile, outdir, whichproc, rhop0, mode, ice, quantize=True):
     print('mode %s' % mode)
     createVariablesPyGeosMie(nc, NUM_EXPAND, oppclassic)
     ang = np.array(nc.variables['ang'][:])
-    elements = {k: np.asarray(nc.variables[k][:]) for k in MISH_KEYS}
+    elements = {k: nc.variables[k] for k in MISH_KEYS}       # decoded lazily, straight into expand_table's input array
     nc.variables['pmom'][:] = expand_table(ang, elements, oppclassic, quantize=quantize)
     nc.close()
     print("%s done" % fn)

@@ -67,6 +67,17 @@ class _Var(object):
                 object.__setattr__(self, "_data", np.zeros(self._shape, dtype=self.dtype))
         return self._data
 
+    def read_into(self, dst):
+        """Decode the variable straight into `dst` (same shape, any strides, native byte order): one pass from the file's pages, no
+        intermediate native copy.  The variable itself stays un-decoded (and is still copied file to file as raw bytes)."""
+        if self._data is not None or self._source is None or self.dtype.kind == "S":
+            np.copyto(dst, self.data)
+            return
+        path, off, be = self._source
+        mm = np.memmap(path, dtype=be, mode="r", offset=off, shape=self._shape)
+        np.copyto(dst, mm)
+        del mm
+
     def untouched_source(self):
         """(path, offset, type) of the bytes in the file this variable was read from, as long as nothing has been assigned to it."""
         return None if self._dirty else self._source
@@ -235,7 +246,14 @@ class _MemDataset(object):
                     if arr.dtype.kind == "S":
                         f.write(arr.tobytes())
                     else:
-                        arr.astype(_NC_TYPES[code]).tofile(f)  # one byte-swapping pass, written straight from the swapped buffer
+                        # byte-swapping pass in cache-sized pieces through one small buffer (no second full-size array)
+                        flat = arr.reshape(-1)
+                        step = 1 << 19
+                        buf = np.empty(min(step, max(flat.size, 1)), dtype=_NC_TYPES[code])
+                        for i in range(0, flat.size, step):
+                            m = min(step, flat.size - i)
+                            buf[:m] = flat[i:i + m]
+                            f.write(memoryview(buf[:m]).cast("B"))
                 if _pad4(nbytes) != nbytes:
                     f.write(b"\0" * (_pad4(nbytes) - nbytes))
         os.replace(tmp, self._path)
