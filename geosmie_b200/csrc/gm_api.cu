@@ -114,8 +114,8 @@ void gm_pool_give(gm_handle_s* h, DevBuf& b) {
   if (!b.p) return;
   size_t held = 0;
   for (const auto& q : h->pool) held += q.cap;
-  if (b.cap < ((size_t)1 << 20) || h->pool.size() >= 12 || held + b.cap > ((size_t)8 << 30)) {
-    b.release();                        // small buffers are cheap to re-create; the pool stays bounded (12 buffers, 8 GB)
+  if (b.cap <= ((size_t)64 << 20) || h->pool.size() >= 32 || held + b.cap > ((size_t)8 << 30)) {
+    b.release();                        // buffers up to 64 MB go to the process-wide cache (gm_common.cuh); the pool stays bounded (32 buffers, 8 GB)
     return;
   }
   h->pool.push_back(b);
@@ -128,6 +128,7 @@ extern "C" int gm_destroy(gm_handle_t h) {
   cudaSetDevice(h->device);
   for (auto& b : h->pool) b.release();
   h->pool.clear();
+  struct Flush { ~Flush() { gm_cache_flush(); } } flush_cache_at_return;   // after every buffer of the handle has been released
   for (auto& b : h->ws) b.release();
   for (DevBuf* b : {&h->scratch_coef, &h->scratch_gact, &h->scratch_scal_part, &h->scratch_part, &h->scratch_g_hpart, &h->scratch_g_hsum,
                     &h->scratch_wphase, &h->scratch_wscal, &h->scratch_taskc, &h->scratch_nodepart})

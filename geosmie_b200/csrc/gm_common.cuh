@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -29,17 +31,87 @@ void gm_set_error(const char* fmt, ...);
   } while (0)
 
 // ------------------------------------------------------------------------------------------------ device buffers
+// Process-wide cache of released device buffers (per device, best fit).  A table build walks through its size bins with one
+// gm_table after the other; each owns ~30 small device arrays, and cudaFree / cudaMalloc of those -- normally 20 us each -- were seen
+// to take milliseconds each in a third of the optics_SS builds on some boxes (gm_table_destroy 0.34 s instead of 3 ms,
+// tools/diag_lut_outliers.py).  Released buffers up to 64 MB are therefore kept (at most 1 GB / 1024 buffers per process) and handed to
+// the next allocation of a similar size; the large per-table outputs go through the handle's pool (gm_pool_*).  All work of the library
+// is ordered on the handle's stream, so a recycled buffer cannot still be in use.  GEOSMIE_NO_ALLOC_CACHE=1 turns the cache off.
+struct GmCacheEntry {
+  void* p;
+  size_t cap;
+  int dev;
+};
+inline std::mutex g_gm_cache_mu;
+inline std::vector<GmCacheEntry> g_gm_cache;
+inline size_t g_gm_cache_bytes = 0;
+inline bool gm_cache_enabled() {
+  static const bool on = getenv("GEOSMIE_NO_ALLOC_CACHE") == nullptr;
+  return on;
+}
+inline void* gm_cache_take(size_t want, size_t* cap) {
+  if (!gm_cache_enabled()) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lk(g_gm_cache_mu);
+  int best = -1;
+  for (int i = 0; i < (int)g_gm_cache.size(); ++i) {
+    const GmCacheEntry& e = g_gm_cache[i];
+    if (e.dev == dev && e.cap >= want && e.cap <= want + want / 2 + 4096 && (best < 0 || e.cap < g_gm_cache[best].cap)) best = i;
+  }
+  if (best < 0) return nullptr;
+  void* p = g_gm_cache[best].p;
+  *cap = g_gm_cache[best].cap;
+  g_gm_cache_bytes -= *cap;
+  g_gm_cache.erase(g_gm_cache.begin() + best);
+  return p;
+}
+inline void gm_cache_put(void* p, size_t cap) {
+  if (!p) return;
+  int dev = 0;
+  if (gm_cache_enabled() && cap <= ((size_t)64 << 20) && cudaGetDevice(&dev) == cudaSuccess) {
+    std::lock_guard<std::mutex> lk(g_gm_cache_mu);
+    if (g_gm_cache.size() < 1024 && g_gm_cache_bytes + cap <= ((size_t)1 << 30)) {
+      g_gm_cache.push_back({p, cap, dev});
+      g_gm_cache_bytes += cap;
+      return;
+    }
+  }
+  cudaFree(p);
+}
+// frees the cached buffers of the current device (gm_destroy)
+inline void gm_cache_flush() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return;
+  std::lock_guard<std::mutex> lk(g_gm_cache_mu);
+  for (size_t i = 0; i < g_gm_cache.size();) {
+    if (g_gm_cache[i].dev == dev) {
+      cudaFree(g_gm_cache[i].p);
+      g_gm_cache_bytes -= g_gm_cache[i].cap;
+      g_gm_cache.erase(g_gm_cache.begin() + i);
+    } else {
+      ++i;
+    }
+  }
+}
+
 // Grow-only device allocation; keeps repeated API calls free of cudaMalloc.
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
   int ensure(size_t bytes) {
     if (bytes <= cap) return GM_OK;
-    if (p) cudaFree(p);
+    gm_cache_put(p, cap);
     p = nullptr;
     cap = 0;
     size_t want = bytes + bytes / 8 + 256;
+    if ((p = gm_cache_take(want, &cap)) != nullptr) return GM_OK;
     cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaErrorMemoryAllocation) {      // give the cached buffers back to the driver and try once more
+      cudaGetLastError();
+      gm_cache_flush();
+      e = cudaMalloc(&p, want);
+    }
     if (e != cudaSuccess) {
       gm_set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
       p = nullptr;
@@ -49,7 +121,7 @@ struct DevBuf {
     return GM_OK;
   }
   void release() {
-    if (p) cudaFree(p);
+    gm_cache_put(p, cap);
     p = nullptr;
     cap = 0;
   }

@@ -235,10 +235,24 @@ class _MemDataset(object):
                 src = v.untouched_source()
                 if src is not None and src[2] == _NC_TYPES[code]:
                     with open(src[0], "rb") as g:           # a variable nobody looked at: raw bytes from file to file
-                        g.seek(src[1])
-                        left = nbytes
+                        left, spos = nbytes, src[1]
+                        if hasattr(os, "copy_file_range") and not os.environ.get("GEOSMIE_NO_COPY_FILE_RANGE"):   # inside the kernel, no bounce through user space
+                            f.flush()
+                            try:
+                                while left:
+                                    n = os.copy_file_range(g.fileno(), f.fileno(), left, spos, begin + nbytes - left)
+                                    if n <= 0:
+                                        break
+                                    left -= n
+                                    spos += n
+                            except OSError:
+                                pass
+                            f.seek(begin + nbytes - left)
+                        g.seek(spos)
                         while left:
                             chunk = g.read(min(left, 1 << 24))
+                            if not chunk:
+                                raise IOError("%s: unexpected end of file while copying variable %r" % (src[0], v.name))
                             f.write(chunk)
                             left -= len(chunk)
                 else:

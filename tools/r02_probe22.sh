@@ -1,5 +1,5 @@
 #!/bin/bash
-# A/B of the host-side file paths (old: astype + tofile, stack; new: chunked swap, read_into) in one call
+# A/B of a host-side file path switch (here: copy_file_range for the untouched variables) in one call, runs alternating
 set -u
 cd "$(dirname "$0")/.."
 cat > /tmp/ab.py <<'PY'
@@ -10,10 +10,10 @@ from geosmie_b200.gsf import rungsf
 sp = sys.argv[1]
 with tempfile.TemporaryDirectory() as d:
     cfg = workloads.write_run_dir(d, sp); os.chdir(d)
-    for attempt in range(9):
+    for attempt in range(11):
         old = attempt % 2 == 1
-        if old: os.environ["GEOSMIE_AB_OLD"] = "1"
-        else: os.environ.pop("GEOSMIE_AB_OLD", None)
+        if old: os.environ["GEOSMIE_NO_COPY_FILE_RANGE"] = "1"
+        else: os.environ.pop("GEOSMIE_NO_COPY_FILE_RANGE", None)
         out = os.path.join(d, "o%d" % attempt); os.makedirs(out)
         with contextlib.redirect_stdout(io.StringIO()):
             t0 = time.perf_counter(); runoptics.main(["--name", cfg, "--dest", out]); t1 = time.perf_counter()
