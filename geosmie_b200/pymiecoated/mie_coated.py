@@ -157,79 +157,56 @@ class MieScatterProps(object):
 
 
 class Mie(object):
-    """Class for computing Mie scattering from homogeneous and coated spheres (mie_coated.py:214-396).
+    """Mie scattering of a homogeneous or coated sphere (mie_coated.py:214-396): the reference's object API on top of the GPU library.
 
-    Attributes / keyword arguments: x, eps, mu, eps2, y, m, m2 (and ajv, ayv) exactly as in the reference; `mc` is
-    accepted as an alias of `m2`.
-    """
+    Keyword arguments / attributes as in the reference: x, y (core and shell size parameters), eps, mu, eps2 (permittivity, permeability,
+    shell permittivity) or m, m2 (refractive indices; `mc` is an alias of `m2`), and the validation inputs ajv, ayv.  Results are cached
+    per parameter set in a mie_aux.Cache, like the reference's."""
+
+    _PLAIN = ("eps", "mu", "eps2")              # stored as given
+    _CHECKED = ("m", "m2", "mc", "x", "y")      # go through the property setters, in this order (y is validated against x)
 
     def __init__(self, **kwargs):
         self._cache = Cache()
-        self.eps = None
-        self.mu = 1.0
-        self._x = None
-        self._y = None
-        self.eps2 = None
-        self.ajv = ()
-        self.ayv = ()
-        for k in ["eps", "mu", "eps2"]:
+        self.eps, self.mu, self.eps2 = None, 1.0, None
+        self._x = self._y = None
+        self.ajv = self.ayv = ()
+        for k in self._PLAIN:
             if k in kwargs:
                 self.__dict__[k] = kwargs[k]
-        if "m" in kwargs:
-            self.m = kwargs["m"]
-        if "m2" in kwargs:
-            self.m2 = kwargs["m2"]
-        if "mc" in kwargs:
-            self.m2 = kwargs["mc"]
-        if "x" in kwargs:
-            self.x = kwargs["x"]
-        if "y" in kwargs:
-            self.y = kwargs["y"]
-        if "ajv" in kwargs:
-            self.ajv = tuple(kwargs["ajv"])
-        if "ayv" in kwargs:
-            self.ayv = tuple(kwargs["ayv"])
+        for k in self._CHECKED:
+            if k in kwargs:
+                setattr(self, k, kwargs[k])
+        for k in ("ajv", "ayv"):
+            if k in kwargs:
+                setattr(self, k, tuple(kwargs[k]))
 
+    # ---- parameters -------------------------------------------------------------------------------------------------
+    def _set_m(self, m):
+        self.mu, self.eps = 1.0, m ** 2
+
+    def _set_m2(self, m2):
+        self.eps2 = m2 ** 2
+
+    def _set_x(self, x):
+        if not x >= 0.0:
+            raise ValueError("The size x cannot be smaller than 0.")
+        self._x = x
+
+    def _set_y(self, y):
+        if not y >= self.x:
+            raise ValueError("The size y cannot be smaller than x.")
+        self._y = y
+
+    m = property(lambda self: sqrt(self.eps / self.mu), _set_m, doc="refractive index sqrt(eps / mu); setting it sets mu = 1")
+    m2 = property(lambda self: sqrt(self.eps2), _set_m2, doc="refractive index of the shell")
+    mc = m2
+    x = property(lambda self: self._x, _set_x, doc="size parameter of the sphere (of the core when y is given)")
+    y = property(lambda self: self._y, _set_y, doc="size parameter of the shell")
+
+    # ---- results ----------------------------------------------------------------------------------------------------
     def _params_signature(self):
         return (self.eps, self.mu, self.x, self.y, self.eps2)
-
-    def qext(self):
-        """The extinction efficiency."""
-        return self._get_scatt_prop("qext")
-
-    def qsca(self):
-        """The scattering efficiency."""
-        return self._get_scatt_prop("qsca")
-
-    def qabs(self):
-        """The absorption efficiency."""
-        return self._get_scatt_prop("qabs")
-
-    def qb(self):
-        """The backscattering efficiency."""
-        return self._get_scatt_prop("qb")
-
-    def asy(self):
-        """The asymmetry parameter, i.e. <cos(theta)>."""
-        return self._get_scatt_prop("asy")
-
-    def qratio(self):
-        """The backscattering ratio, i.e. qb()/qsca()."""
-        return self._get_scatt_prop("qratio")
-
-    def S12(self, u):
-        """The amplitude scattering matrix elements S1 and S2 (Bohren and Huffman conventions) at cosine u."""
-        return self._get_S12(u)
-
-    def S12_array(self, u):
-        """Extension: S1, S2 at an array of cosines in one GPU call."""
-        u = np.asarray(u, dtype=float)
-        if np.any(np.abs(u) > 1):
-            raise ValueError("The cosine u must be between -1 and 1.")
-        return self._entry().S12_array(u)
-
-    def S12_pt(self, pin, tin):
-        return self._get_S12_pt(pin, tin)
 
     def _entry(self):
         sig = self._params_signature()
@@ -240,50 +217,33 @@ class Mie(object):
     def _get_scatt_prop(self, prop):
         return self._entry().prop(prop)
 
-    def _get_S12(self, u):
+    def S12(self, u):
+        """Amplitude scattering matrix elements S1, S2 (Bohren and Huffman conventions) at the cosine u of the scattering angle."""
         if abs(u) > 1:
             raise ValueError("The cosine u must be between -1 and 1.")
         return self._entry().S12(u)
 
-    def _get_S12_pt(self, pin, tin):
+    def S12_array(self, u):
+        """Extension: S1, S2 at an array of cosines in one GPU call."""
+        u = np.asarray(u, dtype=float)
+        if np.any(np.abs(u) > 1):
+            raise ValueError("The cosine u must be between -1 and 1.")
+        return self._entry().S12_array(u)
+
+    def S12_pt(self, pin, tin):
+        """S1, S2 from caller-supplied angle functions pi_n, tau_n (mie_props.py:133-150)."""
         return self._entry().S12_pt(pin, tin)
 
-    def _get_m(self):
-        return sqrt(self.eps / self.mu)
 
-    def _set_m(self, m):
-        self.mu = 1.0
-        self.eps = m ** 2
+def _efficiency(name, what):
+    def f(self):
+        return self._get_scatt_prop(name)
+    f.__name__, f.__doc__ = name, what
+    return f
 
-    m = property(_get_m, _set_m)
 
-    def _get_m2(self):
-        return sqrt(self.eps2)
-
-    def _set_m2(self, m2):
-        self.eps2 = m2 ** 2
-
-    m2 = property(_get_m2, _set_m2)
-    mc = property(_get_m2, _set_m2)
-
-    def _get_x(self):
-        return self._x
-
-    def _set_x(self, x):
-        if x >= 0.0:
-            self._x = x
-        else:
-            raise ValueError("The size x cannot be smaller than 0.")
-
-    x = property(_get_x, _set_x)
-
-    def _get_y(self):
-        return self._y
-
-    def _set_y(self, y):
-        if y >= self.x:
-            self._y = y
-        else:
-            raise ValueError("The size y cannot be smaller than x.")
-
-    y = property(_get_y, _set_y)
+for _name, _what in (("qext", "extinction efficiency"), ("qsca", "scattering efficiency"), ("qabs", "absorption efficiency"),
+                     ("qb", "backscattering efficiency"), ("asy", "asymmetry parameter <cos(theta)>"),
+                     ("qratio", "backscattering ratio qb / qsca")):
+    setattr(Mie, _name, _efficiency(_name, _what))
+del _name, _what
