@@ -624,7 +624,7 @@ __global__ void __launch_bounds__(GM_CONTRACT_THREADS, 1) k_contract(ContractArg
   {
     const unsigned char* gact = A.gact + (size_t)task * A.ngroup;
     for (int g = threadIdx.x; g < ng; g += blockDim.x) {
-      const bool on = gact[cs + g] && !(A.gskip && A.gskip[cs + g]);
+      const bool on = !(A.gskip && A.gskip[cs + g]) && gact[cs + g];   // (gact is not written for the groups the Gram kernels own)
       meta[g] = make_int2(on ? A.gk4[cs + g] : 0, A.grow[cs + g]);
     }
   }
