@@ -175,7 +175,7 @@ struct CoeffArgs {
 // MODE 0: DMMA group layout (c+ = (a+b) f_n sqrt(w), c- = (a-b) f_n sqrt(w)); MODE 1: natural a_n, b_n;
 // MODE 2: like MODE 0 but a_n, b_n are READ from the natural layout (coated spheres, produced by k_coated_coeff).
 #ifndef GM_COEFF_MINB
-#define GM_COEFF_MINB 4   // 16 warps per SM without spills; at 5 (96 registers) the 16-value reduction spills 12 B and the kernel ran 1.9 ms instead of 1.05 ms on some boxes
+#define GM_COEFF_MINB 4   // 16 warps per SM without spills; 5 / 6 (96 / 80 registers, 140 / 328 B of spills) run k_coeff in 99.8 / 126.6 ms instead of 67.8 ms on optics_SS (profiles/r02e_su_tuning_sweep.txt)
 #endif
 // GM_COEFF_TPC (experiment, default 1 = one task per CTA, unchanged code): tasks a CTA works through for its four particle
 // groups.  With 1 the optics_SU step launches 76,860 CTAs of ~8 us each for this kernel; > 1 makes them proportionally fewer and
