@@ -90,6 +90,7 @@ extern "C" int gm_init(int device, gm_handle_t* out) {
   const char* cv = getenv("GEOSMIE_COEFF_CARVEOUT");
   if (cv && !strcmp(cv, "maxl1")) {
     GM_CUDA_TRY(cudaFuncSetAttribute(k_coeff<0>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxL1));
+    GM_CUDA_TRY(cudaFuncSetAttribute((k_coeff<0, GM_COEFF_MINB_LONG>), cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxL1));
     GM_CUDA_TRY(cudaFuncSetAttribute(k_coeff<1>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxL1));
     GM_CUDA_TRY(cudaFuncSetAttribute(k_coeff<2>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxL1));
   }
@@ -897,6 +898,19 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
     if (!big_groups.empty())
       GM_CUDA_TRY(cudaMemcpyAsync(t->s_big.p, big_groups.data(), sizeof(int) * big_groups.size(), cudaMemcpyHostToDevice, st));
   }
+  // k_coeff instantiation: the 168-register build for launches of long groups (gm_mie_kernels.cuh)
+  bool coeff_long = false;
+  {
+    long long rows = 0, cnt = 0;
+    if (use_small) {
+      for (int g : big_groups) rows += 4LL * G.gk4[g], ++cnt;
+    } else {
+      for (int g = 0; g < G.ngroup; ++g) rows += 4LL * G.gk4[g], ++cnt;
+    }
+    coeff_long = cnt > 0 && rows >= (long long)GM_COEFF_LONG_ROWS * cnt;
+    static const char* force = getenv("GEOSMIE_COEFF_LONG");     // experiments: 0 / 1 forces the choice
+    if (force) coeff_long = atoi(force) != 0;
+  }
   if ((rc = t->h->scratch_coef.ensure(per_task_bytes * tb)) || (rc = t->h->scratch_gact.ensure((size_t)tb * G.ngroup)) ||
       (rc = t->h->scratch_scal_part.ensure(sizeof(double) * (size_t)tb * nmode * G.ngroup * GM_NSCAL)) ||
       (rc = t->h->scratch_part.ensure(sizeof(double) * (size_t)tb * nchunk_total * 4 * GM_NANG_PAD)) ||
@@ -1007,9 +1021,17 @@ static int table_run_core(gm_table_t t, int ntask, const double* d_mz, const dou
     } else if (use_small) {
       A.gsel = t->s_big.as<int>();
       A.nsel = (int)big_groups.size();
-      if (A.nsel > 0) k_coeff<0><<<dim3((nt + GM_COEFF_TPC - 1) / GM_COEFF_TPC, (A.nsel + 3) / 4), 128, 0, st>>>(A);
+      if (A.nsel > 0) {
+        if (coeff_long)
+          k_coeff<0, GM_COEFF_MINB_LONG><<<dim3((nt + GM_COEFF_TPC - 1) / GM_COEFF_TPC, (A.nsel + 3) / 4), 128, 0, st>>>(A);
+        else
+          k_coeff<0><<<dim3((nt + GM_COEFF_TPC - 1) / GM_COEFF_TPC, (A.nsel + 3) / 4), 128, 0, st>>>(A);
+      }
     } else {
-      k_coeff<0><<<dim3((nt + GM_COEFF_TPC - 1) / GM_COEFF_TPC, (G.ngroup + 3) / 4), 128, 0, st>>>(A);
+      if (coeff_long)
+        k_coeff<0, GM_COEFF_MINB_LONG><<<dim3((nt + GM_COEFF_TPC - 1) / GM_COEFF_TPC, (G.ngroup + 3) / 4), 128, 0, st>>>(A);
+      else
+        k_coeff<0><<<dim3((nt + GM_COEFF_TPC - 1) / GM_COEFF_TPC, (G.ngroup + 3) / 4), 128, 0, st>>>(A);
     }
     GM_LAUNCH_CHECK(h);
     if ((rc = ev_mark(t, 0))) return rc;

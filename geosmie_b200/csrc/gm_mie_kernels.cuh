@@ -202,8 +202,18 @@ struct CoeffArgs {
   for (int task = blockIdx.x * GM_COEFF_TPC; task < min(A.ntask, (int)(blockIdx.x + 1) * GM_COEFF_TPC); ++task)
 #define GM_COEFF_NEXT_TASK continue
 #endif
-template <int MODE>
-__global__ void __launch_bounds__(128, GM_COEFF_MINB) k_coeff(CoeffArgs A) {
+// MINB = CTAs of 128 threads per SM: 4 (128 registers, 16 warps per SM) for short groups, GM_COEFF_MINB_LONG = 3 (168 registers, 12 warps,
+// no spills) for launches whose groups are long: on optics_SS (mean nmax of the launched groups in the hundreds) the 168-register build
+// runs 58.5 ms instead of 67.8 ms, on optics_SU (nmax 9..40) 0.445 instead of 0.428 ms; 2 (194 registers) is back at 67 ms
+// (profiles/r02e_su_tuning_sweep.txt).  The host picks the instantiation per run from the mean number of rows per launched group.
+#ifndef GM_COEFF_MINB_LONG
+#define GM_COEFF_MINB_LONG 3
+#endif
+#ifndef GM_COEFF_LONG_ROWS
+#define GM_COEFF_LONG_ROWS 64     // mean coefficient rows (orders, padded to 4) per launched group from which the long build is used
+#endif
+template <int MODE, int MINB = GM_COEFF_MINB>
+__global__ void __launch_bounds__(128, MINB) k_coeff(CoeffArgs A) {
   int g = (int)(gridDim.y - 1 - blockIdx.y) * 4 + (threadIdx.x >> 5);
   if (A.gsel) {
     if (g >= A.nsel) return;
