@@ -209,6 +209,9 @@ struct CoeffArgs {
 #ifndef GM_COEFF_MINB_LONG
 #define GM_COEFF_MINB_LONG 3
 #endif
+#ifndef GM_COEFF_PD_LONG
+#define GM_COEFF_PD_LONG 4         // depth of the Riccati-Bessel prefetch ring (= unroll factor of the order loop) of the long build
+#endif
 #ifndef GM_COEFF_LONG_ROWS
 #define GM_COEFF_LONG_ROWS 64     // mean coefficient rows (orders, padded to 4) per launched group from which the long build is used
 #endif
@@ -282,7 +285,7 @@ __global__ void __launch_bounds__(128, MINB) k_coeff(CoeffArgs A) {
   double sext = 0.0, ssca = 0.0, qbr = 0.0, qbi = 0.0, sasy = 0.0;
   // Riccati-Bessel values are fetched PD orders ahead of their use (the table read is the only memory access on the
   // serial recurrence's critical path); the first PD+1 orders are requested before the recurrence starts.
-  constexpr int PD = 4;
+  constexpr int PD = (MODE == 0 && MINB == GM_COEFF_MINB_LONG && GM_COEFF_MINB_LONG != GM_COEFF_MINB) ? GM_COEFF_PD_LONG : 4;
   double qpsi[PD], qchi[PD];
 #pragma unroll
   for (int k = 0; k < PD; ++k) qpsi[k] = qchi[k] = 0.0;
@@ -342,7 +345,7 @@ __global__ void __launch_bounds__(128, MINB) k_coeff(CoeffArgs A) {
     // (unless the per-particle efficiencies are asked for, gm_table_particles: then every particle is evaluated and its rows carry f = 0)
     // `any`: some weight of the lane is non-zero -- the phase weight may be 0 where a (signed) scalar weight is not ('du' grid)
     const bool lane_on = act && (any || A.q != nullptr);
-#pragma unroll 4
+#pragma unroll(PD)
     for (; n >= 1; --n, f2 -= 2.0, pp -= 32, pc -= 32) {
       const double2 ti = crcp(tt);
       const bool on = n < nmx;
